@@ -1,0 +1,224 @@
+"""ctypes view of the CPU oracle (oracle/_build/liboracle.so) and of the reference's own Spec
+compiled unmodified (oracle/_ref/libspec_ref.so).  TEST INFRASTRUCTURE ONLY -- see oracle/oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = _HERE / "_build" / "liboracle.so"
+_REF = _HERE / "_ref" / "libspec_ref.so"
+
+REF_SPECTR_SIZE = 32768  # reference spec.cpp:8
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    if force or not _LIB.exists() or (Path("/root/reference/spec.cpp").exists() and not _REF.exists()):
+        subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
+
+
+_lib = None
+_ref = None
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+class PvParams(C.Structure):
+    _fields_ = [("N", C.c_int), ("hop", C.c_int), ("fs", C.c_double), ("rate", C.c_float),
+                ("rate_per_frame", C.c_void_p)]
+
+
+class Marker(C.Structure):
+    _fields_ = [("sample", C.c_int), ("note", C.c_double), ("dTime", C.c_double),
+                ("pitchBend", C.c_double)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _LIB.exists():
+            build()
+        _lib = C.CDLL(str(_LIB))
+        _lib.mlxo_pv_num_frames.restype = C.c_int64
+        _lib.mlxo_pv_num_frames.argtypes = [C.c_int64, C.c_int]
+        _lib.mlxo_grain_export.restype = C.c_int64
+        _lib.mlxo_sample2time.restype = C.c_double
+        _lib.mlxo_duration.restype = C.c_double
+        _lib.mlxo_time2pitchbend.restype = C.c_float
+    return _lib
+
+
+def have_ref() -> bool:
+    return _REF.exists()
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(str(_REF))
+    return _ref
+
+
+def num_threads() -> int:
+    return int(lib().mlxo_num_threads())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---------------------------------------------------------------- Spec
+def spec_batch(wav: np.ndarray, N: int, start_end: np.ndarray, nthreads: int = 0) -> np.ndarray:
+    wav = np.ascontiguousarray(wav, np.float32)
+    se = np.ascontiguousarray(start_end, np.int32).reshape(-1, 2)
+    out = np.empty((se.shape[0], N // 2), np.float32)
+    rc = lib().mlxo_spec_batch(_ptr(wav), C.c_int64(wav.size), C.c_int(N), _ptr(se),
+                               C.c_int(se.shape[0]), _ptr(out), C.c_int(nthreads))
+    if rc:
+        raise RuntimeError("mlxo_spec_batch failed")
+    return out
+
+
+def ref_spec_run(wav: np.ndarray, start_end: np.ndarray) -> np.ndarray:
+    """The reference's own Spec (N = 32768) driven through getSpec()."""
+    wav = np.ascontiguousarray(wav, np.float32)
+    se = np.ascontiguousarray(start_end, np.int32).reshape(-1, 2)
+    out = np.zeros((se.shape[0], REF_SPECTR_SIZE // 2), np.float32)
+    ln = ref().mlxo_ref_spec_run(_ptr(wav), C.c_longlong(wav.size), _ptr(se), C.c_int(se.shape[0]),
+                                 _ptr(out))
+    if ln != REF_SPECTR_SIZE // 2:
+        raise RuntimeError(f"reference Spec returned length {ln}")
+    return out
+
+
+def colormap(spec: np.ndarray, k: float) -> np.ndarray:
+    spec = np.ascontiguousarray(spec, np.float32)
+    out = np.empty(spec.shape + (3,), np.uint8)
+    lib().mlxo_colormap(_ptr(spec), C.c_int(spec.size), C.c_float(k), _ptr(out))
+    return out
+
+
+# ---------------------------------------------------------------- PV
+def pv_num_frames(n: int, hop: int) -> int:
+    return int(lib().mlxo_pv_num_frames(n, hop))
+
+
+def pv_run(x: np.ndarray, N: int, hop: int, rate: float, fs: float = 48000.0,
+           rate_per_frame: np.ndarray | None = None, want_debug: bool = False,
+           want_audio: bool = True):
+    """Returns dict(y, peak, f0, margin[, inc, smag])."""
+    x = np.ascontiguousarray(x, np.float32)
+    n = x.size
+    F = pv_num_frames(n, hop)
+    nb = N // 2 + 1
+    y = np.zeros(n, np.float32) if want_audio else None
+    peak = np.zeros(F, np.int32)
+    f0 = np.zeros(F, np.float32)
+    margin = np.zeros(F, np.float64)
+    inc = np.zeros((F, nb), np.uint32) if want_debug else None
+    smag = np.zeros((F, nb), np.float32) if want_debug else None
+    rpf = None
+    if rate_per_frame is not None:
+        rpf = np.ascontiguousarray(rate_per_frame, np.float32)
+        assert rpf.size == F
+    p = PvParams(N, hop, fs, np.float32(rate), _ptr(rpf))
+    rc = lib().mlxo_pv_run(_ptr(x), C.c_int64(n), C.byref(p), _ptr(y), _ptr(peak), _ptr(f0),
+                           _ptr(margin), _ptr(inc), _ptr(smag))
+    if rc:
+        raise RuntimeError("mlxo_pv_run failed (N must be a power of two, hop = N/4)")
+    out = dict(y=y, peak=peak, f0=f0, margin=margin)
+    if want_debug:
+        out.update(inc=inc, smag=smag)
+    return out
+
+
+def pv_run_batch(x: np.ndarray, N: int, hop: int, rate: float, fs: float = 48000.0,
+                 nthreads: int = 0):
+    x = np.ascontiguousarray(x, np.float32)
+    ntracks, n = x.shape
+    F = pv_num_frames(n, hop)
+    y = np.zeros_like(x)
+    peak = np.zeros((ntracks, F), np.int32)
+    f0 = np.zeros((ntracks, F), np.float32)
+    p = PvParams(N, hop, fs, np.float32(rate), None)
+    rc = lib().mlxo_pv_run_batch(_ptr(x), C.c_int64(n), C.c_int(ntracks), C.byref(p), _ptr(y),
+                                 _ptr(peak), _ptr(f0), C.c_int(nthreads))
+    if rc:
+        raise RuntimeError("mlxo_pv_run_batch failed")
+    return dict(y=y, peak=peak, f0=f0)
+
+
+def pv_gather_range(j: int, r: float, nbins: int):
+    lo, hi = C.c_int(), C.c_int()
+    lib().mlxo_pv_gather_range(C.c_int(j), C.c_float(r), C.c_int(nbins), C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+# ---------------------------------------------------------------- grains
+def _markers(markers):
+    arr = (Marker * max(1, len(markers)))()
+    for i, m in enumerate(markers):
+        arr[i] = Marker(int(m[0]), float(m[1]), float(m[2]), float(m[3]))
+    return arr, len(markers)
+
+
+def grain_segment(wav: np.ndarray):
+    wav = np.ascontiguousarray(wav, np.float32)
+    cap = max(16, wav.size // 700 + 16)
+    gs = np.zeros(cap, np.int32)
+    gl = np.zeros(cap, np.int32)
+    ng = lib().mlxo_grain_segment(_ptr(wav), C.c_int64(wav.size), _ptr(gs), _ptr(gl), C.c_int(cap))
+    assert ng <= cap
+    return gs[:ng].copy(), gl[:ng].copy()
+
+
+def time2sample(markers, sr: int, val: float) -> int:
+    arr, nm = _markers(markers)
+    return int(lib().mlxo_time2sample(arr, C.c_int(nm), C.c_int(sr), C.c_double(val)))
+
+
+def sample2time(markers, sr: int, val: int) -> float:
+    arr, nm = _markers(markers)
+    return float(lib().mlxo_sample2time(arr, C.c_int(nm), C.c_int(sr), C.c_int(val)))
+
+
+def time2pitchbend(markers, sr: int, n: int, val: float) -> float:
+    arr, nm = _markers(markers)
+    return float(lib().mlxo_time2pitchbend(arr, C.c_int(nm), C.c_int(sr), C.c_int64(n),
+                                           C.c_double(val)))
+
+
+def grain_export(wav: np.ndarray, sr: int, markers, g_start=None, g_len=None):
+    """Returns dict(pcm, pcm16, schedule=dict(gstart, glen, rate, out_off, next))."""
+    wav = np.ascontiguousarray(wav, np.float32)
+    if g_start is None:
+        g_start, g_len = grain_segment(wav)
+    g_start = np.ascontiguousarray(g_start, np.int32)
+    g_len = np.ascontiguousarray(g_len, np.int32)
+    arr, nm = _markers(markers)
+    cap = int(wav.size * 4.5 + 4096)
+    pcm = np.zeros(cap, np.float32)
+    pcm16 = np.zeros(cap, np.int16)
+    caps = g_start.size * 6 + 16
+    sg = np.zeros(caps, np.int32)
+    sl = np.zeros(caps, np.int32)
+    srate = np.zeros(caps, np.float32)
+    soff = np.zeros(caps, np.int64)
+    snext = np.zeros(caps, np.float32)
+    ns = C.c_int()
+    ln = lib().mlxo_grain_export(_ptr(wav), C.c_int64(wav.size), C.c_int(sr), arr, C.c_int(nm),
+                                 _ptr(g_start), _ptr(g_len), C.c_int(g_start.size), _ptr(pcm),
+                                 _ptr(pcm16), C.c_int64(cap), _ptr(sg), _ptr(sl), _ptr(srate),
+                                 _ptr(soff), _ptr(snext), C.byref(ns), C.c_int(caps))
+    assert ln <= cap and ns.value <= caps, (ln, cap, ns.value, caps)
+    k = ns.value
+    return dict(pcm=pcm[:ln].copy(), pcm16=pcm16[:ln].copy(),
+                schedule=dict(gstart=sg[:k].copy(), glen=sl[:k].copy(), rate=srate[:k].copy(),
+                              out_off=soff[:k].copy(), next=snext[:k].copy()))
