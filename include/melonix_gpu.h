@@ -1,0 +1,139 @@
+/* include/melonix_gpu.h -- C ABI of libmelonix_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for melonix's one data-parallel hot path.  The reference
+ * (mika314/melonix) has no FFI; its boundary is the C++ class surface `Spec` / `SpecCache`
+ * (reference spec.hpp:11-39, spec-cache.hpp:13-39) plus the private resynthesis loop
+ * App::process / App::exportWav (reference app.cpp:294-345, 1194-1215).  The host-side C++ mirror
+ * of those classes (melonix_b200/host/) and every other binding (Python ctypes in melonix_b200/,
+ * see INTEGRATION.md) reach the GPU only through the functions declared here.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the boundary; every function returns MLX_OK (0) or a
+ *     negative mlx_status and leaves a message retrievable with mlx_last_error() (thread-local).
+ *   - there is NO CPU fallback: without a CUDA device of compute capability 10.x mlx_create fails.
+ *   - calls on one mlx_ctx must be serialised by the caller (the host `Spec` calls from its single
+ *     worker thread).  Work is issued on the context's stream (mlx_set_stream) and is asynchronous
+ *     for the *_dev entry points until mlx_sync(); host-pointer entry points return when done.
+ *   - "frame f" follows the reference's Spec job convention (spec.cpp:47, spec-cache.cpp:63-65):
+ *     it covers samples [(f+1)*hop - fftN, (f+1)*hop), zero outside [0, n); F = ceil(n / hop).
+ */
+#ifndef MELONIX_GPU_H
+#define MELONIX_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MLX_API __attribute__((visibility("default")))
+#else
+#define MLX_API
+#endif
+
+typedef enum {
+  MLX_OK = 0,
+  MLX_ERR_INVALID = -1,     /* bad argument                                      */
+  MLX_ERR_CUDA = -2,        /* CUDA runtime error (message has the detail)        */
+  MLX_ERR_NOMEM = -3,       /* device or host allocation failed                   */
+  MLX_ERR_STATE = -4,       /* call order violated (e.g. no tracks uploaded)       */
+  MLX_ERR_UNSUPPORTED = -5  /* size / ratio outside what the kernels implement     */
+} mlx_status;
+
+typedef struct mlx_ctx mlx_ctx; /* opaque: device buffers, tables, stream, scratch */
+
+/* ---- context ------------------------------------------------------------------------------ */
+MLX_API int mlx_create(mlx_ctx **out, int device);
+MLX_API void mlx_destroy(mlx_ctx *ctx);
+MLX_API const char *mlx_last_error(void);
+/* cuda_stream: a cudaStream_t (NULL = the legacy default stream). */
+MLX_API int mlx_set_stream(mlx_ctx *ctx, void *cuda_stream);
+MLX_API int mlx_sync(mlx_ctx *ctx);
+/* sm_count, cc = major*10+minor, total device memory in bytes. Any pointer may be NULL. */
+MLX_API int mlx_device_info(mlx_ctx *ctx, int *sm_count, int *cc, size_t *total_mem);
+/* number of kernels launched by this context since creation (bench.py's gpu_launches). */
+MLX_API int64_t mlx_launch_count(const mlx_ctx *ctx);
+
+/* ---- tracks ------------------------------------------------------------------------------- */
+/* Replaces Spec::Spec(std::span<float> wav) (reference spec.cpp:10-16): the reference keeps a
+ * non-owning view of the mono track; here the samples are copied once into HBM, zero-padded on
+ * both sides so that the reference's "outside [0,n) reads as 0" rule (spec.cpp:50-54) needs no
+ * branches in the phase-vocoder kernels.  wav[t] points at n[t] floats (host memory). */
+MLX_API int mlx_upload_tracks(mlx_ctx *ctx, const float *const *wav, const int64_t *n, int ntracks);
+/* Same, from device memory (device-to-device copy on the context stream). */
+MLX_API int mlx_upload_tracks_dev(mlx_ctx *ctx, const float *const *wav_dev, const int64_t *n, int ntracks);
+MLX_API int mlx_num_tracks(const mlx_ctx *ctx);
+MLX_API int64_t mlx_track_len(const mlx_ctx *ctx, int track);
+
+/* ---- Spec path: STFT magnitude (replaces Spec::internalGetSpec, reference spec.cpp:44-66) ---- */
+/* `count` jobs (start,end) exactly as passed to Spec::getSpec (spec.cpp:18): window [end-fftN,end),
+ * samples before `start` decayed by expf(-2.5e-4f*(start-i)), outside [0,n) zero; output row j =
+ * fftN/2 floats |FFT|/fftN (Nyquist bin dropped).  fftN in {512,...,32768}; the reference's
+ * SpectrSize is 32768 (spec.cpp:8).  start_end = [count][2] int32, out = [count][fftN/2]. */
+MLX_API int mlx_spec_batch(mlx_ctx *ctx, int track, int fftN, const int32_t *start_end, int count,
+                   float *out);
+MLX_API int mlx_spec_batch_dev(mlx_ctx *ctx, int track, int fftN, const int32_t *start_end_dev, int count,
+                       float *out_dev);
+/* Regular-hop jobs generated on the device: job f = (f*hop, (f+1)*hop), f in
+ * [first_frame, first_frame+count).  out_dev = [count][fftN/2]. */
+MLX_API int mlx_spec_frames_dev(mlx_ctx *ctx, int track, int fftN, int hop, int64_t first_frame,
+                        int64_t count, float *out_dev);
+/* Spec + the colour ramp of SpecCache::populateTex fused (reference spec-cache.cpp:77-96):
+ * out_rgb = [count][fftN/2][3] bytes, k = the brightness gain (spec-cache.cpp:79). */
+MLX_API int mlx_spec_batch_rgb(mlx_ctx *ctx, int track, int fftN, const int32_t *start_end, int count,
+                       float k, uint8_t *out_rgb);
+
+/* ---- phase-vocoder path (NOT IN REFERENCE; PV-spec v1) --------------------------- */
+typedef struct {
+  int fftN;            /* 512, 1024, 2048, 4096 or 8192                                        */
+  int hop;             /* must be fftN / 4                                                      */
+  float rate;          /* pitch ratio, host powf(2.f, semitones/12.f) as reference app.cpp:297  */
+  double sample_rate;  /* for f0 and the 50..2000 Hz peak-search band                           */
+  /* optional per-track device arrays [F] of per-frame ratios (NULL, or entries NULL -> rate)   */
+  const float *const *rate_per_frame_dev;
+  /* time-range sharding (multi-GPU): only frames [frame_begin, frame_end) are owned by this
+   * call; -1,-1 = all.  With frame_begin > 0 the track buffer must hold the halo frame
+   * frame_begin-1 and output hops [frame_begin, frame_end) are written.                        */
+  int64_t frame_begin, frame_end;
+  /* accumulated synthesis phase carried in from earlier frames of the same track: per-track
+   * device arrays of fftN/2+1 uint32 (NULL, or entries NULL -> 0).                              */
+  const uint32_t *const *phase_in_dev;
+  /* L2-tiling budget in MiB for the analysis->synthesis intermediates; 0 = library default,
+   * <0 = one wave over the whole range.                                                          */
+  int wave_mib;
+} mlx_pv_params;
+
+/* Full pipeline on the uploaded tracks.  Per-track outputs (entries or whole arrays may be NULL):
+ * out_wav[t]: n[t] floats; out_peak[t]: F[t] int32 peak bins; out_f0[t]: F[t] floats (Hz).
+ * Only elements belonging to frames/hops in [frame_begin, frame_end) are written. */
+MLX_API int mlx_pv_run(mlx_ctx *ctx, const mlx_pv_params *p, float *const *out_wav, int32_t *const *out_peak,
+               float *const *out_f0);
+MLX_API int mlx_pv_run_dev(mlx_ctx *ctx, const mlx_pv_params *p, float *const *out_wav_dev,
+                   int32_t *const *out_peak_dev, float *const *out_f0_dev);
+/* Analysis only over [frame_begin, frame_end): writes the per-track phase totals of the owned
+ * frames (fftN/2+1 uint32 each, device) -- the quantity ranks exchange when one file is sharded
+ * by time range -- plus peak / f0. */
+MLX_API int mlx_pv_phase_totals_dev(mlx_ctx *ctx, const mlx_pv_params *p, uint32_t *const *totals_dev,
+                            int32_t *const *out_peak_dev, float *const *out_f0_dev);
+/* End-to-end convenience for host buffers: uploads `wav`, runs, downloads, with the copies of
+ * track t+1 / t-1 overlapped with the kernels of track t on separate streams. */
+MLX_API int mlx_pv_process_host(mlx_ctx *ctx, const mlx_pv_params *p, const float *const *wav,
+                        const int64_t *n, int ntracks, float *const *out_wav,
+                        int32_t *const *out_peak, float *const *out_f0);
+
+/* ---- grain path (replaces the inner loop of App::process, reference app.cpp:331-343, and the
+ *      float->int16 conversion of App::exportWav, app.cpp:1209-1212) ---------------------------- */
+/* The schedule (one row per App::process call that produced audio) is computed on the host by the
+ * caller (melonix_b200/host/grain_schedule.hpp mirrors exportWav's cursor recurrence):
+ *   g_start/g_len: the grain [start, start+len) in the track; g_rate: powf(2, pitchBend/12);
+ *   out_off[ngrains+1]: output offset of each row (last = total rendered length);
+ *   g_next: first sample of the grain that follows in output time (app.cpp:312-329).
+ * out / out_i16 (either may be NULL): total_len = out_off[ngrains] + tail_zeros samples. */
+MLX_API int mlx_grain_render(mlx_ctx *ctx, int track, const int32_t *g_start, const int32_t *g_len,
+                     const float *g_rate, const int64_t *out_off, const float *g_next, int ngrains,
+                     int tail_zeros, float *out, int16_t *out_i16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MELONIX_GPU_H */

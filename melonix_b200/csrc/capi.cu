@@ -1,0 +1,691 @@
+// melonix_b200/csrc/capi.cu -- the extern "C" layer declared in include/melonix_gpu.h.
+//
+// Owns the device copy of the tracks, twiddle/window tables, scratch for the phase-vocoder
+// intermediates and the stream; translates the C calls into kernel launches.  There is no CPU path:
+// every entry point either launches sm_100a kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/melonix_gpu.h"
+#include "kernels.h"
+
+using namespace mlx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(e_ == cudaErrorMemoryAllocation ? MLX_ERR_NOMEM : MLX_ERR_CUDA,         \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t want) {
+    if (want <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct Tables {
+  DevBuf tw_d, twr_d, tw_f, twr_f, win, wsyn;
+  bool pv_ready = false, spec_ready = false;
+};
+
+struct Track {
+  size_t offset = 0;  // floats from the base of the track buffer to sample 0
+  int64_t n = 0;
+};
+
+}  // namespace
+
+struct mlx_ctx {
+  int device = 0;
+  int sm_count = 0, cc = 0;
+  size_t total_mem = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of mlx_pv_process_host
+  int64_t launches = 0;
+
+  DevBuf track_buf;
+  std::vector<Track> tracks;
+
+  std::map<int, Tables> tables;
+
+  // phase-vocoder scratch
+  DevBuf smag, lacc, tot, pre, carry, track_desc, ptr_stage;
+  DevBuf out_wav, out_peak, out_f0;  // device results for the host-pointer entry points
+  DevBuf jobs, spec_out, spec_rgb;
+  DevBuf g_i32a, g_i32b, g_f32a, g_f32b, g_i64, g_out, g_out16;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+
+  const float* track_ptr(int t) const { return static_cast<const float*>(track_buf.p) + tracks[t].offset; }
+};
+
+namespace {
+
+int reserve_pinned(mlx_ctx* c, size_t bytes) {
+  if (bytes <= c->pinned_bytes) return MLX_OK;
+  if (c->pinned) cudaFreeHost(c->pinned);
+  c->pinned = nullptr;
+  c->pinned_bytes = 0;
+  CK(cudaMallocHost(&c->pinned, bytes));
+  c->pinned_bytes = bytes;
+  return MLX_OK;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <typename T>
+int upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
+  CK(b.reserve(v.size() * sizeof(T)));
+  CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // v is a temporary
+  return MLX_OK;
+}
+
+// Tables are computed in double on the host (cos/sin at exact angles) and rounded once.
+int ensure_tables(mlx_ctx* c, int N, bool want_pv, Tables** out) {
+  Tables& tb = c->tables[N];
+  const int NC = N / 2;
+  if (!tb.spec_ready) {
+    std::vector<cplx<float>> twf(NC), twrf(NC / 2 + 1);
+    for (int m = 0; m < NC; ++m) {
+      const double a = 2.0 * M_PI * (double)m / (double)NC;
+      twf[m] = cplx<float>{(float)std::cos(a), (float)-std::sin(a)};
+    }
+    for (int k = 0; k <= NC / 2; ++k) {
+      const double a = 2.0 * M_PI * (double)k / (double)N;
+      twrf[k] = cplx<float>{(float)std::cos(a), (float)-std::sin(a)};
+    }
+    int rc;
+    if ((rc = upload_vec(tb.tw_f, twf, c->stream))) return rc;
+    if ((rc = upload_vec(tb.twr_f, twrf, c->stream))) return rc;
+    CK(spec_configure(N));
+    tb.spec_ready = true;
+  }
+  if (want_pv && !tb.pv_ready) {
+    std::vector<cplx<double>> twd(NC), twrd(NC / 2 + 1);
+    for (int m = 0; m < NC; ++m) {
+      const double a = 2.0 * M_PI * (double)m / (double)NC;
+      twd[m] = cplx<double>{std::cos(a), -std::sin(a)};
+    }
+    for (int k = 0; k <= NC / 2; ++k) {
+      const double a = 2.0 * M_PI * (double)k / (double)N;
+      twrd[k] = cplx<double>{std::cos(a), -std::sin(a)};
+    }
+    // PV-spec A.1: periodic Hann computed in double, stored as float; A.7: g = H / sum w^2 (float)
+    std::vector<float> win(N), wsyn(N);
+    double sw2 = 0.0;
+    for (int j = 0; j < N; ++j) {
+      win[j] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)j / (double)N));
+      sw2 += (double)win[j] * (double)win[j];
+    }
+    const float g = (float)((double)(N / 4) / sw2);
+    for (int j = 0; j < N; ++j) wsyn[j] = (float)((double)g * (double)win[j] / (double)N);
+    int rc;
+    if ((rc = upload_vec(tb.tw_d, twd, c->stream))) return rc;
+    if ((rc = upload_vec(tb.twr_d, twrd, c->stream))) return rc;
+    if ((rc = upload_vec(tb.win, win, c->stream))) return rc;
+    if ((rc = upload_vec(tb.wsyn, wsyn, c->stream))) return rc;
+    CK(pv_configure(N));
+    tb.pv_ready = true;
+  }
+  *out = &tb;
+  return MLX_OK;
+}
+
+int layout_tracks(mlx_ctx* c, const int64_t* n, int ntracks) {
+  if (ntracks <= 0 || !n) return fail(MLX_ERR_INVALID, "ntracks must be > 0");
+  c->tracks.assign(ntracks, Track{});
+  size_t off = 0;
+  for (int t = 0; t < ntracks; ++t) {
+    if (n[t] < 0 || n[t] > (int64_t)0x7fffffff - 65536)
+      return fail(MLX_ERR_INVALID, "track length must be in [0, 2^31 - 65536) samples (reference indexes with int)");
+    c->tracks[t].offset = off + kPadFront;
+    c->tracks[t].n = n[t];
+    size_t len = (size_t)kPadFront + (size_t)n[t] + (size_t)kPadBack;
+    len = (len + 31) & ~size_t(31);  // keep every track 128-byte aligned (TMA needs 16)
+    off += len;
+  }
+  CK(c->track_buf.reserve(off * sizeof(float)));
+  CK(cudaMemsetAsync(c->track_buf.p, 0, off * sizeof(float), c->stream));
+  return MLX_OK;
+}
+
+int64_t num_frames(int64_t n, int hop) { return (n + hop - 1) / hop; }
+
+struct PvPlan {
+  int N, H, G, NBP;
+  int CA, CS;
+  int64_t fb, fe, Fmax;
+  int64_t wave_frames;
+};
+
+int pv_validate(mlx_ctx* c, const mlx_pv_params* p, PvPlan* pl) {
+  if (!c || !p) return fail(MLX_ERR_INVALID, "null argument");
+  if (c->tracks.empty()) return fail(MLX_ERR_STATE, "no tracks uploaded");
+  const int N = p->fftN;
+  if (!is_pow2(N) || N < 512 || N > kPvMaxN) return fail(MLX_ERR_UNSUPPORTED, "fftN must be 512..8192 (power of two)");
+  if (p->hop * 4 != N) return fail(MLX_ERR_UNSUPPORTED, "hop must be fftN/4 (osamp = 4)");
+  if (!(p->rate >= 0.25f && p->rate <= 4.0f)) return fail(MLX_ERR_UNSUPPORTED, "rate must be in [0.25, 4]");
+  if (!(p->sample_rate > 0)) return fail(MLX_ERR_INVALID, "sample_rate must be > 0");
+  pl->N = N;
+  pl->H = p->hop;
+  pl->G = pv_group_count(N);
+  pl->NBP = pv_nbp(N);
+  int64_t Fmax = 0;
+  for (auto& t : c->tracks) Fmax = std::max(Fmax, num_frames(t.n, p->hop));
+  pl->Fmax = Fmax;
+  pl->fb = p->frame_begin < 0 ? 0 : p->frame_begin;
+  pl->fe = p->frame_end < 0 ? Fmax : std::min<int64_t>(p->frame_end, Fmax);
+  if (pl->fb > pl->fe) return fail(MLX_ERR_INVALID, "frame_begin > frame_end");
+  // frames per CTA including halo frames: a multiple of G
+  int chunk = 128;
+  if (const char* e = getenv("MLX_PV_CHUNK")) chunk = std::max(8, atoi(e));
+  const int64_t span = std::max<int64_t>(1, pl->fe - pl->fb);
+  // keep at least ~4 CTAs per SM in flight when the job is small
+  while (chunk > 16 && (span / chunk) * (int64_t)c->tracks.size() < 4LL * c->sm_count) chunk /= 2;
+  int m = std::max(1, chunk / pl->G);
+  while (pl->G * m - 3 < 1) ++m;
+  pl->CA = pl->G * m - 1;
+  pl->CS = pl->G * m - 3;
+  // wave size
+  int mib = p->wave_mib;
+  if (mib == 0) {
+    mib = 96;
+    if (const char* e = getenv("MLX_PV_WAVE_MIB")) mib = atoi(e);
+  }
+  if (mib < 0) {
+    pl->wave_frames = span;
+  } else {
+    const double per_frame = (double)c->tracks.size() * pl->NBP * 8.0;
+    int64_t wf = (int64_t)((double)mib * 1048576.0 / per_frame) - 3;
+    wf = std::max<int64_t>(wf, pl->CA);
+    pl->wave_frames = std::min<int64_t>(wf, span);
+  }
+  return MLX_OK;
+}
+
+// Runs waves of K_A -> scan (-> K_S) over frames [fb, fe) of all uploaded tracks.
+int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth, float* const* out_wav,
+               int32_t* const* out_peak, float* const* out_f0, uint32_t* const* totals_dev) {
+  Tables* tb = nullptr;
+  int rc = ensure_tables(c, pl.N, true, &tb);
+  if (rc) return rc;
+  const int nt = (int)c->tracks.size();
+  const size_t rows = (size_t)pl.wave_frames + 3;
+  const size_t nchunksA_max = (size_t)((pl.wave_frames + 3 + pl.CA - 1) / pl.CA);
+  CK(c->smag.reserve(sizeof(float) * nt * rows * pl.NBP));
+  CK(c->lacc.reserve(sizeof(uint32_t) * nt * rows * pl.NBP));
+  CK(c->tot.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
+  CK(c->pre.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
+  CK(c->carry.reserve(sizeof(uint32_t) * nt * pl.NBP));
+  CK(c->track_desc.reserve(sizeof(PvTrack) * nt));
+  rc = reserve_pinned(c, sizeof(PvTrack) * nt);
+  if (rc) return rc;
+
+  // the previous call's descriptors may still be in flight from pinned memory
+  CK(cudaStreamSynchronize(c->stream));
+  PvTrack* desc = static_cast<PvTrack*>(c->pinned);
+  for (int t = 0; t < nt; ++t) {
+    desc[t].x = c->track_ptr(t);
+    desc[t].n = c->tracks[t].n;
+    desc[t].F = num_frames(c->tracks[t].n, pl.H);
+    desc[t].out = (synth && out_wav) ? out_wav[t] : nullptr;
+    desc[t].peak = out_peak ? out_peak[t] : nullptr;
+    desc[t].f0 = out_f0 ? out_f0[t] : nullptr;
+    desc[t].rate_pf = p->rate_per_frame_dev ? p->rate_per_frame_dev[t] : nullptr;
+  }
+  CK(cudaMemcpyAsync(c->track_desc.p, desc, sizeof(PvTrack) * nt, cudaMemcpyHostToDevice, c->stream));
+
+  // carry-in phase
+  CK(cudaMemsetAsync(c->carry.p, 0, sizeof(uint32_t) * nt * pl.NBP, c->stream));
+  if (p->phase_in_dev) {
+    for (int t = 0; t < nt; ++t)
+      if (p->phase_in_dev[t])
+        CK(cudaMemcpyAsync(static_cast<uint32_t*>(c->carry.p) + (size_t)t * pl.NBP, p->phase_in_dev[t],
+                           sizeof(uint32_t) * (pl.N / 2 + 1), cudaMemcpyDeviceToDevice, c->stream));
+  }
+
+  PvTables pt{static_cast<const cplx<double>*>(tb->tw_d.p), static_cast<const cplx<double>*>(tb->twr_d.p),
+              static_cast<const cplx<float>*>(tb->tw_f.p),  static_cast<const cplx<float>*>(tb->twr_f.p),
+              static_cast<const float*>(tb->win.p),         static_cast<const float*>(tb->wsyn.p)};
+  PvScratch sc{static_cast<float*>(c->smag.p), static_cast<uint32_t*>(c->lacc.p), static_cast<uint32_t*>(c->tot.p),
+               static_cast<uint32_t*>(c->pre.p), static_cast<uint32_t*>(c->carry.p)};
+  const PvTrack* tdev = static_cast<const PvTrack*>(c->track_desc.p);
+
+  int kmin = (int)std::ceil(50.0 * pl.N / p->sample_rate), kmax = (int)std::floor(2000.0 * pl.N / p->sample_rate);
+  kmin = std::max(kmin, 1);
+  kmax = std::min(kmax, pl.N / 2);
+  kmax = std::max(kmax, kmin);
+
+  for (int64_t wb = pl.fb; wb < pl.fe; wb += pl.wave_frames) {
+    PvWave wv{};
+    wv.wb = wb;
+    wv.we = std::min<int64_t>(wb + pl.wave_frames, pl.fe);
+    wv.rows = (int)rows;
+    wv.CA = pl.CA;
+    wv.nchunksA = (int)((wv.we + 3 - wv.wb + pl.CA - 1) / pl.CA);
+    wv.CS = pl.CS;
+    wv.nchunksS = (int)((wv.we - wv.wb + pl.CS - 1) / pl.CS);
+    wv.rate = p->rate;
+    wv.fs_over_N = (float)(p->sample_rate / (double)pl.N);
+    wv.kmin = kmin;
+    wv.kmax = kmax;
+    CK(launch_pv_analyze(pl.N, tdev, nt, wv, pt, sc, c->stream));
+    CK(launch_pv_scan(pl.N, nt, wv, sc, c->stream));
+    c->launches += 2;
+    if (synth) {
+      CK(launch_pv_synth(pl.N, tdev, nt, wv, pt, sc, c->stream));
+      c->launches += 1;
+    }
+  }
+  if (totals_dev) {
+    for (int t = 0; t < nt; ++t)
+      if (totals_dev[t])
+        CK(cudaMemcpyAsync(totals_dev[t], static_cast<uint32_t*>(c->carry.p) + (size_t)t * pl.NBP,
+                           sizeof(uint32_t) * (pl.N / 2 + 1), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return MLX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mlx_last_error(void) { return g_err.c_str(); }
+
+int mlx_create(mlx_ctx** out, int device) {
+  if (!out) return fail(MLX_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(MLX_ERR_CUDA, std::string("no CUDA device: melonix_b200 has no CPU fallback (") +
+                                  cudaGetErrorString(e) + ")");
+  if (device < 0 || device >= ndev) return fail(MLX_ERR_INVALID, "device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(MLX_ERR_UNSUPPORTED, std::string("kernels are built for sm_100a only; device is ") + prop.name);
+  mlx_ctx* c = new mlx_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc = prop.major * 10 + prop.minor;
+  c->total_mem = prop.totalGlobalMem;
+  if (cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return fail(MLX_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  *out = c;
+  return MLX_OK;
+}
+
+void mlx_destroy(mlx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (DevBuf* b : {&c->track_buf, &c->smag, &c->lacc, &c->tot, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
+                    &c->out_wav, &c->out_peak, &c->out_f0, &c->jobs, &c->spec_out, &c->spec_rgb, &c->g_i32a,
+                    &c->g_i32b, &c->g_f32a, &c->g_f32b, &c->g_i64, &c->g_out, &c->g_out16})
+    b->release();
+  for (auto& kv : c->tables)
+    for (DevBuf* b : {&kv.second.tw_d, &kv.second.twr_d, &kv.second.tw_f, &kv.second.twr_f, &kv.second.win,
+                      &kv.second.wsyn})
+      b->release();
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  delete c;
+}
+
+int mlx_set_stream(mlx_ctx* c, void* cuda_stream) {
+  if (!c) return fail(MLX_ERR_INVALID, "ctx is null");
+  c->stream = static_cast<cudaStream_t>(cuda_stream);
+  return MLX_OK;
+}
+
+int mlx_sync(mlx_ctx* c) {
+  if (!c) return fail(MLX_ERR_INVALID, "ctx is null");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+int mlx_device_info(mlx_ctx* c, int* sm_count, int* cc, size_t* total_mem) {
+  if (!c) return fail(MLX_ERR_INVALID, "ctx is null");
+  if (sm_count) *sm_count = c->sm_count;
+  if (cc) *cc = c->cc;
+  if (total_mem) *total_mem = c->total_mem;
+  return MLX_OK;
+}
+
+int64_t mlx_launch_count(const mlx_ctx* c) { return c ? c->launches : 0; }
+
+int mlx_upload_tracks(mlx_ctx* c, const float* const* wav, const int64_t* n, int ntracks) {
+  if (!c || !wav) return fail(MLX_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  int rc = layout_tracks(c, n, ntracks);
+  if (rc) return rc;
+  for (int t = 0; t < ntracks; ++t)
+    if (n[t] > 0)
+      CK(cudaMemcpyAsync(static_cast<float*>(c->track_buf.p) + c->tracks[t].offset, wav[t], sizeof(float) * n[t],
+                         cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+int mlx_upload_tracks_dev(mlx_ctx* c, const float* const* wav_dev, const int64_t* n, int ntracks) {
+  if (!c || !wav_dev) return fail(MLX_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  int rc = layout_tracks(c, n, ntracks);
+  if (rc) return rc;
+  for (int t = 0; t < ntracks; ++t)
+    if (n[t] > 0)
+      CK(cudaMemcpyAsync(static_cast<float*>(c->track_buf.p) + c->tracks[t].offset, wav_dev[t],
+                         sizeof(float) * n[t], cudaMemcpyDeviceToDevice, c->stream));
+  return MLX_OK;
+}
+
+int mlx_num_tracks(const mlx_ctx* c) { return c ? (int)c->tracks.size() : 0; }
+int64_t mlx_track_len(const mlx_ctx* c, int t) {
+  return (c && t >= 0 && t < (int)c->tracks.size()) ? c->tracks[t].n : -1;
+}
+
+// ------------------------------------------------------------------------------------------------ Spec
+static int spec_common(mlx_ctx* c, int track, int fftN, const int* jobs_dev, int hop, int64_t first_frame,
+                       int64_t count, float* out_dev, unsigned char* rgb_dev, float k) {
+  if (!c) return fail(MLX_ERR_INVALID, "ctx is null");
+  if (track < 0 || track >= (int)c->tracks.size()) return fail(MLX_ERR_STATE, "track not uploaded");
+  if (!is_pow2(fftN) || fftN < 512 || fftN > 32768)
+    return fail(MLX_ERR_UNSUPPORTED, "fftN must be a power of two in [512, 32768]");
+  if (count < 0) return fail(MLX_ERR_INVALID, "count < 0");
+  CK(cudaSetDevice(c->device));
+  Tables* tb = nullptr;
+  int rc = ensure_tables(c, fftN, false, &tb);
+  if (rc) return rc;
+  SpecArgs a{};
+  a.x = c->track_ptr(track);
+  a.n = c->tracks[track].n;
+  a.jobs = jobs_dev;
+  a.hop = hop;
+  a.first_frame = first_frame;
+  a.count = count;
+  a.out = out_dev;
+  a.rgb = rgb_dev;
+  a.kcol = k;
+  a.tw_f = static_cast<const cplx<float>*>(tb->tw_f.p);
+  a.twr_f = static_cast<const cplx<float>*>(tb->twr_f.p);
+  CK(launch_spec(fftN, a, c->stream));
+  if (count > 0) c->launches += 1;
+  return MLX_OK;
+}
+
+int mlx_spec_batch_dev(mlx_ctx* c, int track, int fftN, const int32_t* start_end_dev, int count, float* out_dev) {
+  if (!start_end_dev || !out_dev) return fail(MLX_ERR_INVALID, "null argument");
+  return spec_common(c, track, fftN, start_end_dev, 0, 0, count, out_dev, nullptr, 0.f);
+}
+
+int mlx_spec_frames_dev(mlx_ctx* c, int track, int fftN, int hop, int64_t first_frame, int64_t count,
+                        float* out_dev) {
+  if (!out_dev || hop <= 0) return fail(MLX_ERR_INVALID, "bad argument");
+  return spec_common(c, track, fftN, nullptr, hop, first_frame, count, out_dev, nullptr, 0.f);
+}
+
+int mlx_spec_batch(mlx_ctx* c, int track, int fftN, const int32_t* start_end, int count, float* out) {
+  if (!c || !start_end || !out) return fail(MLX_ERR_INVALID, "null argument");
+  if (count <= 0) return count == 0 ? MLX_OK : fail(MLX_ERR_INVALID, "count < 0");
+  CK(cudaSetDevice(c->device));
+  CK(c->jobs.reserve(sizeof(int32_t) * 2 * (size_t)count));
+  CK(c->spec_out.reserve(sizeof(float) * (size_t)count * (fftN / 2)));
+  CK(cudaMemcpyAsync(c->jobs.p, start_end, sizeof(int32_t) * 2 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+  int rc = spec_common(c, track, fftN, static_cast<const int*>(c->jobs.p), 0, 0, count,
+                       static_cast<float*>(c->spec_out.p), nullptr, 0.f);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, c->spec_out.p, sizeof(float) * (size_t)count * (fftN / 2), cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+int mlx_spec_batch_rgb(mlx_ctx* c, int track, int fftN, const int32_t* start_end, int count, float k,
+                       uint8_t* out_rgb) {
+  if (!c || !start_end || !out_rgb) return fail(MLX_ERR_INVALID, "null argument");
+  if (count <= 0) return count == 0 ? MLX_OK : fail(MLX_ERR_INVALID, "count < 0");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)count * (fftN / 2) * 3;
+  CK(c->jobs.reserve(sizeof(int32_t) * 2 * (size_t)count));
+  CK(c->spec_rgb.reserve(bytes));
+  CK(cudaMemcpyAsync(c->jobs.p, start_end, sizeof(int32_t) * 2 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+  int rc = spec_common(c, track, fftN, static_cast<const int*>(c->jobs.p), 0, 0, count, nullptr,
+                       static_cast<unsigned char*>(c->spec_rgb.p), k);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_rgb, c->spec_rgb.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ PV
+int mlx_pv_run_dev(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav_dev, int32_t* const* out_peak_dev,
+                   float* const* out_f0_dev) {
+  PvPlan pl{};
+  int rc = pv_validate(c, p, &pl);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  return pv_execute(c, p, pl, true, out_wav_dev, out_peak_dev, out_f0_dev, nullptr);
+}
+
+int mlx_pv_phase_totals_dev(mlx_ctx* c, const mlx_pv_params* p, uint32_t* const* totals_dev,
+                            int32_t* const* out_peak_dev, float* const* out_f0_dev) {
+  PvPlan pl{};
+  int rc = pv_validate(c, p, &pl);
+  if (rc) return rc;
+  if (!totals_dev) return fail(MLX_ERR_INVALID, "totals_dev is null");
+  CK(cudaSetDevice(c->device));
+  mlx_pv_params q = *p;
+  q.phase_in_dev = nullptr;  // totals are relative to the first owned frame
+  return pv_execute(c, &q, pl, false, nullptr, out_peak_dev, out_f0_dev, totals_dev);
+}
+
+int mlx_pv_run(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav, int32_t* const* out_peak,
+               float* const* out_f0) {
+  PvPlan pl{};
+  int rc = pv_validate(c, p, &pl);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  const int nt = (int)c->tracks.size();
+  // device result buffers, one slab per kind
+  std::vector<size_t> woff(nt + 1, 0), foff(nt + 1, 0);
+  for (int t = 0; t < nt; ++t) {
+    woff[t + 1] = woff[t] + (((size_t)c->tracks[t].n + 31) & ~size_t(31));
+    foff[t + 1] = foff[t] + (((size_t)num_frames(c->tracks[t].n, pl.H) + 31) & ~size_t(31));
+  }
+  if (out_wav) CK(c->out_wav.reserve(sizeof(float) * std::max<size_t>(woff[nt], 1)));
+  if (out_peak) CK(c->out_peak.reserve(sizeof(int32_t) * std::max<size_t>(foff[nt], 1)));
+  if (out_f0) CK(c->out_f0.reserve(sizeof(float) * std::max<size_t>(foff[nt], 1)));
+  std::vector<float*> dw(nt, nullptr), df(nt, nullptr);
+  std::vector<int32_t*> dp(nt, nullptr);
+  for (int t = 0; t < nt; ++t) {
+    if (out_wav && out_wav[t]) dw[t] = static_cast<float*>(c->out_wav.p) + woff[t];
+    if (out_peak && out_peak[t]) dp[t] = static_cast<int32_t*>(c->out_peak.p) + foff[t];
+    if (out_f0 && out_f0[t]) df[t] = static_cast<float*>(c->out_f0.p) + foff[t];
+  }
+  rc = pv_execute(c, p, pl, true, out_wav ? dw.data() : nullptr, out_peak ? dp.data() : nullptr,
+                  out_f0 ? df.data() : nullptr, nullptr);
+  if (rc) return rc;
+  // copy back only what this call owns: hops / frames [fb, fe)
+  for (int t = 0; t < nt; ++t) {
+    const int64_t F = num_frames(c->tracks[t].n, pl.H);
+    const int64_t f0 = std::min(pl.fb, F), f1 = std::min(pl.fe, F);
+    if (f1 <= f0) continue;
+    const int64_t s0 = f0 * pl.H, s1 = std::min<int64_t>(f1 * pl.H, c->tracks[t].n);
+    if (dw[t] && s1 > s0)
+      CK(cudaMemcpyAsync(out_wav[t] + s0, dw[t] + s0, sizeof(float) * (s1 - s0), cudaMemcpyDeviceToHost, c->stream));
+    if (dp[t])
+      CK(cudaMemcpyAsync(out_peak[t] + f0, dp[t] + f0, sizeof(int32_t) * (f1 - f0), cudaMemcpyDeviceToHost,
+                         c->stream));
+    if (df[t])
+      CK(cudaMemcpyAsync(out_f0[t] + f0, df[t] + f0, sizeof(float) * (f1 - f0), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* wav, const int64_t* n, int ntracks,
+                        float* const* out_wav, int32_t* const* out_peak, float* const* out_f0) {
+  if (!c || !p || !wav || !n || ntracks <= 0) return fail(MLX_ERR_INVALID, "bad argument");
+  if (p->frame_begin > 0 || p->frame_end >= 0 || p->phase_in_dev || p->rate_per_frame_dev)
+    return fail(MLX_ERR_UNSUPPORTED, "mlx_pv_process_host handles whole tracks with a constant rate");
+  CK(cudaSetDevice(c->device));
+  int rc = layout_tracks(c, n, ntracks);
+  if (rc) return rc;
+  std::vector<Track> all = c->tracks;  // the pipeline runs the kernels one track at a time
+  std::vector<size_t> woff(ntracks + 1, 0), foff(ntracks + 1, 0);
+  for (int t = 0; t < ntracks; ++t) {
+    woff[t + 1] = woff[t] + (((size_t)n[t] + 31) & ~size_t(31));
+    foff[t + 1] = foff[t] + (((size_t)num_frames(n[t], p->hop) + 31) & ~size_t(31));
+  }
+  CK(c->out_wav.reserve(sizeof(float) * std::max<size_t>(woff[ntracks], 1)));
+  CK(c->out_peak.reserve(sizeof(int32_t) * std::max<size_t>(foff[ntracks], 1)));
+  CK(c->out_f0.reserve(sizeof(float) * std::max<size_t>(foff[ntracks], 1)));
+  std::vector<cudaEvent_t> ev_in(ntracks), ev_done(ntracks);
+  for (int t = 0; t < ntracks; ++t) {
+    cudaEventCreateWithFlags(&ev_in[t], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_done[t], cudaEventDisableTiming);
+  }
+  cudaEvent_t ev_zero;
+  cudaEventCreateWithFlags(&ev_zero, cudaEventDisableTiming);
+  cudaEventRecord(ev_zero, c->stream);  // padding memset (layout_tracks) precedes the uploads
+  cudaStreamWaitEvent(c->s_in, ev_zero, 0);
+  int result = MLX_OK;
+  for (int t = 0; t < ntracks && result == MLX_OK; ++t) {
+    if (n[t] > 0 &&
+        cudaMemcpyAsync(static_cast<float*>(c->track_buf.p) + all[t].offset, wav[t], sizeof(float) * n[t],
+                        cudaMemcpyHostToDevice, c->s_in) != cudaSuccess)
+      result = fail(MLX_ERR_CUDA, "H2D copy failed");
+    cudaEventRecord(ev_in[t], c->s_in);
+  }
+  for (int t = 0; t < ntracks && result == MLX_OK; ++t) {
+    cudaStreamWaitEvent(c->stream, ev_in[t], 0);
+    c->tracks.assign(1, all[t]);
+    PvPlan pl{};
+    result = pv_validate(c, p, &pl);
+    if (result) break;
+    float* dw = (out_wav && out_wav[t]) ? static_cast<float*>(c->out_wav.p) + woff[t] : nullptr;
+    int32_t* dp = (out_peak && out_peak[t]) ? static_cast<int32_t*>(c->out_peak.p) + foff[t] : nullptr;
+    float* df = (out_f0 && out_f0[t]) ? static_cast<float*>(c->out_f0.p) + foff[t] : nullptr;
+    result = pv_execute(c, p, pl, true, &dw, &dp, &df, nullptr);
+    if (result) break;
+    cudaEventRecord(ev_done[t], c->stream);
+    cudaStreamWaitEvent(c->s_out, ev_done[t], 0);
+    const int64_t F = num_frames(n[t], p->hop);
+    if (dw && n[t] > 0) cudaMemcpyAsync(out_wav[t], dw, sizeof(float) * n[t], cudaMemcpyDeviceToHost, c->s_out);
+    if (dp && F > 0) cudaMemcpyAsync(out_peak[t], dp, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, c->s_out);
+    if (df && F > 0) cudaMemcpyAsync(out_f0[t], df, sizeof(float) * F, cudaMemcpyDeviceToHost, c->s_out);
+  }
+  c->tracks = all;
+  cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_out),
+              e3 = cudaStreamSynchronize(c->s_in);
+  for (int t = 0; t < ntracks; ++t) {
+    cudaEventDestroy(ev_in[t]);
+    cudaEventDestroy(ev_done[t]);
+  }
+  cudaEventDestroy(ev_zero);
+  if (result) return result;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+    return fail(MLX_ERR_CUDA, std::string("pipeline failed: ") +
+                                  cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+  return MLX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ grains
+int mlx_grain_render(mlx_ctx* c, int track, const int32_t* g_start, const int32_t* g_len, const float* g_rate,
+                     const int64_t* out_off, const float* g_next, int ngrains, int tail_zeros, float* out,
+                     int16_t* out_i16) {
+  if (!c || ngrains < 0 || tail_zeros < 0) return fail(MLX_ERR_INVALID, "bad argument");
+  if (track < 0 || track >= (int)c->tracks.size()) return fail(MLX_ERR_STATE, "track not uploaded");
+  if (ngrains > 0 && (!g_start || !g_len || !g_rate || !out_off || !g_next))
+    return fail(MLX_ERR_INVALID, "null schedule");
+  CK(cudaSetDevice(c->device));
+  const int64_t n = c->tracks[track].n;
+  int64_t zero_off = 0;
+  const int64_t rendered = ngrains > 0 ? out_off[ngrains] : 0;
+  for (int g = 0; g < ngrains; ++g) {
+    if (g_start[g] < 0 || g_len[g] <= 0 || (int64_t)g_start[g] + g_len[g] > n || out_off[g + 1] < out_off[g])
+      return fail(MLX_ERR_INVALID, "schedule row outside the track");
+    // every sample a row renders must index inside its grain (reference stops at idx >= size)
+    const int64_t cnt = out_off[g + 1] - out_off[g];
+    if (cnt > 0 && (int64_t)truncf((float)(cnt - 1) * g_rate[g]) >= g_len[g])
+      return fail(MLX_ERR_INVALID, "schedule row renders past its grain");
+  }
+  const int64_t total = rendered + tail_zeros;
+  if (total == 0) return MLX_OK;
+  const size_t ng1 = (size_t)std::max(ngrains, 1);
+  CK(c->g_i32a.reserve(sizeof(int32_t) * ng1));
+  CK(c->g_i32b.reserve(sizeof(int32_t) * ng1));
+  CK(c->g_f32a.reserve(sizeof(float) * ng1));
+  CK(c->g_f32b.reserve(sizeof(float) * ng1));
+  CK(c->g_i64.reserve(sizeof(int64_t) * (ng1 + 1)));
+  if (out) CK(c->g_out.reserve(sizeof(float) * total));
+  if (out_i16) CK(c->g_out16.reserve(sizeof(int16_t) * total));
+  if (ngrains > 0) {
+    CK(cudaMemcpyAsync(c->g_i32a.p, g_start, sizeof(int32_t) * ngrains, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->g_i32b.p, g_len, sizeof(int32_t) * ngrains, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->g_f32a.p, g_rate, sizeof(float) * ngrains, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->g_f32b.p, g_next, sizeof(float) * ngrains, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->g_i64.p, out_off, sizeof(int64_t) * (ngrains + 1), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CK(cudaMemcpyAsync(c->g_i64.p, &zero_off, sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  }
+  GrainArgs a{};
+  a.x = c->track_ptr(track);
+  a.g_start = static_cast<const int*>(c->g_i32a.p);
+  a.g_len = static_cast<const int*>(c->g_i32b.p);
+  a.g_rate = static_cast<const float*>(c->g_f32a.p);
+  a.g_next = static_cast<const float*>(c->g_f32b.p);
+  a.out_off = static_cast<const long long*>(c->g_i64.p);
+  a.ngrains = ngrains;
+  a.total = total;
+  a.out = out ? static_cast<float*>(c->g_out.p) : nullptr;
+  a.out_i16 = out_i16 ? static_cast<short*>(c->g_out16.p) : nullptr;
+  CK(launch_grain(a, c->stream));
+  c->launches += 1;
+  if (out) CK(cudaMemcpyAsync(out, c->g_out.p, sizeof(float) * total, cudaMemcpyDeviceToHost, c->stream));
+  if (out_i16)
+    CK(cudaMemcpyAsync(out_i16, c->g_out16.p, sizeof(int16_t) * total, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+}  // extern "C"

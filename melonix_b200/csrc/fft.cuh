@@ -1,0 +1,321 @@
+// melonix_b200/csrc/fft.cuh
+//
+// Batched power-of-two complex FFT held entirely in shared memory + registers (no cuFFT).
+// Stockham autosort, decimation in time.  A "group" of TPF = NC/16 threads transforms one frame of
+// NC complex points; every thread keeps 16 points in registers, so each stage is one radix-16 (or,
+// for the last stage, 16/R radix-R) butterfly per thread followed by an exchange through the
+// frame's shared-memory buffer.  Stage plan: log2(NC) = 4a + b  ->  a radix-16 stages, then one
+// radix-2^b stage.  The last stage is in place (reads and writes the same thread-private slots).
+//
+// Register slot m of thread t always corresponds to element index (t + m*TPF): that is the layout
+// of the input handed to run() and of the natural-order output it returns.
+//
+// Shared-memory layout: array-of-complex (8 B for float, 16 B for double) with one padding element
+// every 16 (pad(i) = i + i/16).  With 64/128-bit accesses issued per half/quarter warp this makes
+// the stride-16 stores of the radix-16 stages and all unit-stride loads bank-conflict free.
+//
+// The file is also compiled by g++ (tests/host/fft_emul.cpp) with a sequential emulation of the
+// thread group, which is how the index arithmetic is verified without a GPU.
+#pragma once
+
+#ifdef __CUDACC__
+#define MLX_HD __host__ __device__ __forceinline__
+#define MLX_D __device__ __forceinline__
+#define MLX_HDC __host__ __device__ constexpr
+#else
+#define MLX_HD inline
+#define MLX_D inline
+#define MLX_HDC constexpr
+#endif
+
+namespace mlx {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) cplx {
+  T x, y;
+};
+
+template <typename T>
+MLX_HD cplx<T> cmul(const cplx<T> a, const cplx<T> b) {
+  return cplx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T>
+MLX_HD cplx<T> cadd(const cplx<T> a, const cplx<T> b) {
+  return cplx<T>{a.x + b.x, a.y + b.y};
+}
+template <typename T>
+MLX_HD cplx<T> csub(const cplx<T> a, const cplx<T> b) {
+  return cplx<T>{a.x - b.x, a.y - b.y};
+}
+// multiply by DIR*i  (DIR = -1: forward transform, e^{-i...};  DIR = +1: inverse)
+template <int DIR, typename T>
+MLX_HD cplx<T> cmul_i(const cplx<T> a) {
+  return DIR < 0 ? cplx<T>{a.y, -a.x} : cplx<T>{-a.y, a.x};
+}
+
+MLX_HDC int fft_pad(int i) { return i + (i >> 4); }
+
+// ---------------------------------------------------------------- small in-register DFTs
+template <int DIR, typename T>
+MLX_HD void dft2(cplx<T>& a, cplx<T>& b) {
+  const cplx<T> s = cadd(a, b), d = csub(a, b);
+  a = s;
+  b = d;
+}
+
+template <int DIR, typename T>
+MLX_HD void dft4(cplx<T>& a0, cplx<T>& a1, cplx<T>& a2, cplx<T>& a3) {
+  const cplx<T> s02 = cadd(a0, a2), d02 = csub(a0, a2);
+  const cplx<T> s13 = cadd(a1, a3), d13 = cmul_i<DIR>(csub(a1, a3));
+  a0 = cadd(s02, s13);
+  a1 = cadd(d02, d13);
+  a2 = csub(s02, s13);
+  a3 = csub(d02, d13);
+}
+
+// multiply by exp(DIR * 2*pi*i * m / 16), m a compile-time constant
+template <int DIR, int M16, typename T>
+MLX_HD cplx<T> cmul_w16(const cplx<T> a) {
+  constexpr int m = ((M16 % 16) + 16) % 16;
+  if constexpr (m == 0) {
+    return a;
+  } else if constexpr (m == 4) {
+    return cmul_i<DIR>(a);
+  } else if constexpr (m == 8) {
+    return cplx<T>{-a.x, -a.y};
+  } else if constexpr (m == 12) {
+    return cmul_i<-DIR>(a);
+  } else if constexpr (m % 2 == 0) {  // odd multiples of pi/4
+    constexpr T h = T(0.70710678118654752440084436210485L);
+    // (a.x + i a.y) * (c + i s) with |c| = |s| = h
+    constexpr int q = m / 2;  // 1,3,5,7
+    constexpr T c = (q == 1 || q == 7) ? h : -h;
+    constexpr T s0 = (q == 1 || q == 3) ? h : -h;  // sin(2 pi m/16) sign
+    constexpr T s = DIR > 0 ? s0 : -s0;
+    return cplx<T>{a.x * c - a.y * s, a.x * s + a.y * c};
+  } else {
+    constexpr T c1 = T(0.92387953251128675612818318939679L);  // cos(pi/8)
+    constexpr T s1 = T(0.38268343236508977172845998403040L);  // sin(pi/8)
+    // cos/sin(2 pi m / 16) for odd m
+    constexpr T c = (m == 1 || m == 15) ? c1 : (m == 3 || m == 13) ? s1 : (m == 5 || m == 11) ? -s1 : -c1;
+    constexpr T s0 = (m == 1 || m == 7) ? s1 : (m == 3 || m == 5) ? c1 : (m == 9 || m == 15) ? -s1 : -c1;
+    constexpr T s = DIR > 0 ? s0 : -s0;
+    return cplx<T>{a.x * c - a.y * s, a.x * s + a.y * c};
+  }
+}
+
+template <int DIR, typename T>
+MLX_HD void dft8(cplx<T> (&v)[8]) {
+  // n = 2a + b, k = c + 4d
+  dft4<DIR>(v[0], v[2], v[4], v[6]);  // y_0[c] -> v[0],v[2],v[4],v[6]
+  dft4<DIR>(v[1], v[3], v[5], v[7]);  // y_1[c] -> v[1],v[3],v[5],v[7]
+  const cplx<T> y0[4] = {v[0], v[2], v[4], v[6]};
+  cplx<T> y1[4] = {v[1], cmul_w16<DIR, 2>(v[3]), cmul_w16<DIR, 4>(v[5]), cmul_w16<DIR, 6>(v[7])};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    v[c] = cadd(y0[c], y1[c]);
+    v[c + 4] = csub(y0[c], y1[c]);
+  }
+}
+
+template <int DIR, typename T>
+MLX_HD void dft16(cplx<T> (&v)[16]) {
+  // n = 4a + b, k = c + 4d:  y_b[c] = DFT4_a x[4a+b];  y_b[c] *= W16^{bc};  X[c+4d] = DFT4_b y_b[c]
+  dft4<DIR>(v[0], v[4], v[8], v[12]);   // b = 0: y_0[c] in v[4c]
+  dft4<DIR>(v[1], v[5], v[9], v[13]);   // b = 1: y_1[c] in v[4c+1]
+  dft4<DIR>(v[2], v[6], v[10], v[14]);  // b = 2
+  dft4<DIR>(v[3], v[7], v[11], v[15]);  // b = 3
+  // twiddles W16^{b c}: element v[4c + b]
+  v[5] = cmul_w16<DIR, 1>(v[5]);
+  v[6] = cmul_w16<DIR, 2>(v[6]);
+  v[7] = cmul_w16<DIR, 3>(v[7]);
+  v[9] = cmul_w16<DIR, 2>(v[9]);
+  v[10] = cmul_w16<DIR, 4>(v[10]);
+  v[11] = cmul_w16<DIR, 6>(v[11]);
+  v[13] = cmul_w16<DIR, 3>(v[13]);
+  v[14] = cmul_w16<DIR, 6>(v[14]);
+  v[15] = cmul_w16<DIR, 9>(v[15]);
+  // for each c: DFT4 over b of v[4c + b] -> X[c + 4d] ; result d lands in v[4c + d]
+  dft4<DIR>(v[0], v[1], v[2], v[3]);
+  dft4<DIR>(v[4], v[5], v[6], v[7]);
+  dft4<DIR>(v[8], v[9], v[10], v[11]);
+  dft4<DIR>(v[12], v[13], v[14], v[15]);
+  // now v[4c + d] = X[c + 4d]: transpose the 4x4 index to natural order
+  cplx<T> t;
+#define MLX_SWAP(i, j) t = v[i]; v[i] = v[j]; v[j] = t;
+  MLX_SWAP(1, 4) MLX_SWAP(2, 8) MLX_SWAP(3, 12) MLX_SWAP(6, 9) MLX_SWAP(7, 13) MLX_SWAP(11, 14)
+#undef MLX_SWAP
+}
+
+template <int R, int DIR, typename T>
+MLX_HD void dft_r(cplx<T> (&v)[R]) {
+  if constexpr (R == 2) dft2<DIR>(v[0], v[1]);
+  else if constexpr (R == 4) dft4<DIR>(v[0], v[1], v[2], v[3]);
+  else if constexpr (R == 8) dft8<DIR>(v);
+  else dft16<DIR>(v);
+}
+
+// v[r] *= w^r, r = 1..R-1
+template <int R, typename T>
+MLX_HD void twiddle_powers(cplx<T> (&v)[R], const cplx<T> w) {
+  if constexpr (R == 2) {
+    v[1] = cmul(v[1], w);
+  } else if constexpr (R == 4) {
+    const cplx<T> w2 = cmul(w, w);
+    v[1] = cmul(v[1], w);
+    v[2] = cmul(v[2], w2);
+    v[3] = cmul(v[3], cmul(w2, w));
+  } else if constexpr (sizeof(T) == 8) {
+    // double: linear recurrence is accurate to ~R ulp(double), far more than needed
+    cplx<T> p = w;
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+      v[r] = cmul(v[r], p);
+      if (r + 1 < R) p = cmul(p, w);
+    }
+  } else {
+    // float: product tree of depth <= 4 keeps the twiddle error at a few ulp
+    const cplx<T> w2 = cmul(w, w), w3 = cmul(w2, w), w4 = cmul(w2, w2);
+    const cplx<T> w5 = cmul(w4, w), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+    v[1] = cmul(v[1], w);
+    v[2] = cmul(v[2], w2);
+    v[3] = cmul(v[3], w3);
+    v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], w5);
+    v[6] = cmul(v[6], w6);
+    v[7] = cmul(v[7], w7);
+    if constexpr (R == 16) {
+      const cplx<T> w8 = cmul(w4, w4);
+      v[8] = cmul(v[8], w8);
+      v[9] = cmul(v[9], cmul(w8, w));
+      v[10] = cmul(v[10], cmul(w8, w2));
+      v[11] = cmul(v[11], cmul(w8, w3));
+      v[12] = cmul(v[12], cmul(w8, w4));
+      v[13] = cmul(v[13], cmul(w8, w5));
+      v[14] = cmul(v[14], cmul(w8, w6));
+      v[15] = cmul(v[15], cmul(w8, w7));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- plan
+template <int NC>
+struct FftPlan {
+  static_assert(NC >= 256 && (NC & (NC - 1)) == 0, "NC must be a power of two >= 256");
+  static MLX_HDC int log2nc() {
+    int l = 0;
+    while ((1 << l) < NC) ++l;
+    return l;
+  }
+  static constexpr int LOG = log2nc();
+  static constexpr int A = LOG / 4;  // radix-16 stages
+  static constexpr int B = LOG % 4;  // last stage radix 2^B (absent when B == 0)
+  static constexpr int NSTAGES = A + (B ? 1 : 0);
+  static constexpr int TPF = NC / 16;              // threads per frame
+  static constexpr int BUF = NC + NC / 16;         // padded complex elements per frame buffer
+  static MLX_HDC int radix(int s) { return s < A ? 16 : (1 << B); }
+  static MLX_HDC int ns(int s) { return s < A ? (1 << (4 * s)) : (1 << (4 * A)); }
+  // twiddle registers: one per butterfly per stage >= 1
+  static MLX_HDC int nw() {
+    int n = 0;
+    for (int s = 1; s < NSTAGES; ++s) n += 16 / radix(s);
+    return n;
+  }
+  static constexpr int NW = nw() > 0 ? nw() : 1;
+  static MLX_HDC int woff(int s) {
+    int n = 0;
+    for (int q = 1; q < s; ++q) n += 16 / radix(q);
+    return n;
+  }
+};
+
+// Per-thread twiddles (constant across frames): w[woff(s) + b] = exp(DIR*2*pi*i*k/(NS*R)),
+// k = (t + b*TPF) mod NS.  `table[m] = exp(-2*pi*i*m/NC)` (forward), m in [0, NC).
+template <typename T, int NC, int DIR>
+struct FftTwiddles {
+  using P = FftPlan<NC>;
+  cplx<T> w[P::NW];
+  MLX_HD void init(int t, const cplx<T>* table) {
+#pragma unroll
+    for (int s = 1; s < P::NSTAGES; ++s) {
+      const int R = P::radix(s), NS = P::ns(s), BPT = 16 / R;
+#pragma unroll
+      for (int b = 0; b < BPT; ++b) {
+        const int j = t + b * P::TPF;
+        const int k = j & (NS - 1);
+        cplx<T> v = table[k * (NC / (NS * R))];
+        if (DIR > 0) v.y = -v.y;
+        w[P::woff(s) + b] = v;
+      }
+    }
+  }
+};
+
+template <typename T, int NC, int DIR>
+struct Fft {
+  using P = FftPlan<NC>;
+  using C = cplx<T>;
+  static constexpr int TPF = P::TPF;
+
+  // load slot m <- buf[t + m*TPF]
+  static MLX_HD void load(C (&x)[16], const C* buf, int t) {
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] = buf[fft_pad(t + m * TPF)];
+  }
+  // store slot m -> buf[t + m*TPF]
+  static MLX_HD void store(const C (&x)[16], C* buf, int t) {
+#pragma unroll
+    for (int m = 0; m < 16; ++m) buf[fft_pad(t + m * TPF)] = x[m];
+  }
+
+  // butterflies of stage S on the register slots; non-last stages scatter to buf, the last stage
+  // leaves natural-order results in the slots.
+  template <int S>
+  static MLX_HD void compute(C (&x)[16], C* buf, int t, const FftTwiddles<T, NC, DIR>& tw) {
+    constexpr int R = P::radix(S), NS = P::ns(S), BPT = 16 / R;
+    constexpr bool LAST = (S == P::NSTAGES - 1);
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) {
+      C v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = x[b + r * BPT];
+      if constexpr (S > 0) twiddle_powers<R>(v, tw.w[P::woff(S) + b]);
+      dft_r<R, DIR>(v);
+      if constexpr (LAST) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[b + r * BPT] = v[r];
+      } else {
+        const int j = t + b * TPF;
+        const int k = j & (NS - 1);
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[fft_pad(j0 + r * NS)] = v[r];
+      }
+    }
+  }
+
+#ifdef __CUDACC__
+  // Full transform for one thread of the group.  in: x[m] = in[t + m*TPF]; out: x[m] = out[t + m*TPF].
+  // `buf` must not be in use by the group when run() is entered.  Bar::sync() synchronises the group.
+  template <int S, class Bar>
+  static __device__ __forceinline__ void run_from(C (&x)[16], C* buf, int t,
+                                                  const FftTwiddles<T, NC, DIR>& tw, Bar& bar) {
+    if constexpr (S < P::NSTAGES) {
+      if constexpr (S > 0) {
+        bar.sync();  // stage S-1 stores visible
+        load(x, buf, t);
+        if constexpr (S < P::NSTAGES - 1) bar.sync();  // all loads done before anyone overwrites
+      }
+      compute<S>(x, buf, t, tw);
+      run_from<S + 1>(x, buf, t, tw, bar);
+    }
+  }
+  template <class Bar>
+  static __device__ __forceinline__ void run(C (&x)[16], C* buf, int t,
+                                             const FftTwiddles<T, NC, DIR>& tw, Bar& bar) {
+    run_from<0>(x, buf, t, tw, bar);
+  }
+#endif
+};
+
+}  // namespace mlx

@@ -1,0 +1,102 @@
+// melonix_b200/csrc/kernels.h -- internal launch interface between capi.cu and the kernel TUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft.cuh"
+
+namespace mlx {
+
+// Zero padding kept in HBM around every uploaded track so that frames / TMA tiles that reach
+// outside [0, n) read zeros without branches (reference rule: spec.cpp:50-54).
+constexpr int kPadFront = 8192;   // >= max fftN of the phase-vocoder path
+constexpr int kPadBack = 16384;   // >= fftN + one batch of hops
+constexpr int kPvMaxN = 8192;
+
+struct PvTrack {
+  const float* x;          // sample 0 of the padded device copy
+  long long n;             // samples
+  long long F;             // frames = ceil(n / hop)
+  float* out;              // [n] or nullptr
+  int* peak;               // [F] or nullptr
+  float* f0;               // [F] or nullptr
+  const float* rate_pf;    // [F] or nullptr
+};
+
+// Twiddle / window tables for one fftN (device pointers, built on the host in double).
+struct PvTables {
+  const cplx<double>* tw_d;   // exp(-2 pi i m / NC), m in [0, NC)       NC = fftN/2
+  const cplx<double>* twr_d;  // exp(-2 pi i k / fftN), k in [0, NC/2]
+  const cplx<float>* tw_f;
+  const cplx<float>* twr_f;
+  const float* win;           // periodic Hann, float, [fftN]
+  const float* wsyn;          // gain * win / fftN  (synthesis window incl. irfft 1/N), [fftN]
+};
+
+// One wave = owned frame window [wb, we) of every track; intermediates live in `rows` scratch rows
+// per track (rows = we - wb + 3: the three frames after `we` are analysed again for overlap-add).
+struct PvWave {
+  long long wb, we;
+  int rows;
+  int CA, nchunksA;  // analysis chunk (frames per CTA) and chunks per track
+  int CS, nchunksS;  // synthesis chunk (hops per CTA)
+  float rate;
+  float fs_over_N;
+  int kmin, kmax;
+};
+
+struct PvScratch {
+  float* smag;      // [ntracks][rows][NBP]  shifted magnitudes
+  uint32_t* lacc;   // [ntracks][rows][NBP]  chunk-local inclusive phase sums
+  uint32_t* tot;    // [ntracks][nchunksA][NBP] chunk totals over frames < we
+  uint32_t* pre;    // [ntracks][nchunksA][NBP] exclusive prefix (incl. carry)
+  uint32_t* carry;  // [ntracks][NBP] running phase at frame wb (updated to `we` by the scan)
+};
+
+constexpr int pv_nbp(int fftN) { return fftN / 2 + 32; }
+int pv_group_count(int fftN);        // frames per batch (G)
+int pv_threads(int fftN);
+size_t pv_analyze_smem(int fftN);
+size_t pv_synth_smem(int fftN);
+
+cudaError_t launch_pv_analyze(int fftN, const PvTrack* tracks_dev, int ntracks, const PvWave& wv,
+                              const PvTables& tb, const PvScratch& sc, cudaStream_t st);
+cudaError_t launch_pv_scan(int fftN, int ntracks, const PvWave& wv, const PvScratch& sc,
+                           cudaStream_t st);
+cudaError_t launch_pv_synth(int fftN, const PvTrack* tracks_dev, int ntracks, const PvWave& wv,
+                            const PvTables& tb, const PvScratch& sc, cudaStream_t st);
+cudaError_t pv_configure(int fftN);  // cudaFuncSetAttribute for the instantiation
+
+// ---- Spec
+struct SpecArgs {
+  const float* x;       // sample 0 of the padded device copy
+  long long n;
+  const int* jobs;      // [count][2] (start,end) or nullptr -> regular hop
+  int hop;
+  long long first_frame;
+  long long count;
+  float* out;           // [count][fftN/2] or nullptr
+  unsigned char* rgb;   // [count][fftN/2][3] or nullptr
+  float kcol;
+  const cplx<float>* tw_f;
+  const cplx<float>* twr_f;
+};
+cudaError_t spec_configure(int fftN);
+cudaError_t launch_spec(int fftN, const SpecArgs& a, cudaStream_t st);
+
+// ---- grains
+struct GrainArgs {
+  const float* x;
+  const int* g_start;
+  const int* g_len;
+  const float* g_rate;
+  const long long* out_off;  // [ngrains + 1]
+  const float* g_next;
+  int ngrains;
+  long long total;           // out_off[ngrains] + tail zeros
+  float* out;
+  short* out_i16;
+};
+cudaError_t launch_grain(const GrainArgs& a, cudaStream_t st);
+
+}  // namespace mlx
