@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- phase-vocoder frames/sec (2048-FFT, hop 512, 48 kHz mono) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU implementation of the same path, host cores
+
+A "step" is one pass of the whole hot path (K_A analysis -> scan -> K_S synthesis) over
+one batch of synthetic tracks.  Workload = BASELINE.json configs[2]: 64 mono tracks x 5 min per GPU,
+2048-FFT / 512-hop, +3 semitones (tracks shard across GPUs with no data-path collective: weak
+scaling, every rank processes its own 64 tracks).  Inputs (3.7 GB) and outputs (3.7 GB) per GPU are
+far larger than the 126 MB L2, so no flush is needed between timed steps.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM (CUDA
+events, max over ranks); `e2e` = the same through the host-buffer C-ABI call with pinned host input
+and output, copies inside the timed region; `roofline` = algorithmic bytes (8*hop+8 per frame,
+SURVEY.md section 8d) over the summed device time of the path's kernels, against the measured HBM
+peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+FS = 48000
+FFT_N = 2048
+HOP = 512
+SEMITONES = 3.0
+METRIC = "phase-vocoder frames/sec (2048-FFT, hop 512, 48 kHz mono)"
+ALGO_BYTES_PER_FRAME = 8 * HOP + 8  # 4H in + 4H out + peakBin i32 + f0 f32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tracks", type=int, default=64, help="tracks per GPU")
+    ap.add_argument("--seconds", type=float, default=300.0, help="seconds per track")
+    ap.add_argument("--wave-mib", type=int, default=0, help="L2-tiling budget (0 = library default, <0 = off)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline")
+    return ap.parse_args()
+
+
+def semitone_ratio(st):
+    return np.float32(np.power(np.float32(2.0), np.float32(st) / np.float32(12.0), dtype=np.float32))
+
+
+def vibrato_track_numpy(seconds, seed, f_base=220.0):
+    """cfg-2/3 signal (tests/signals.py:vibrato_tone), used for the CPU sample."""
+    n = int(round(seconds * FS))
+    t = np.arange(n) / FS
+    f0 = f_base * 2.0 ** (np.sin(2 * np.pi * 0.5 * t) / 12.0)
+    ph = 2 * np.pi * np.cumsum(f0) / FS
+    x = np.zeros(n)
+    for h in range(1, 9):
+        x += np.sin(h * ph) / h
+    x *= 0.5 / np.abs(x).max()
+    x += np.random.default_rng(seed).standard_normal(n) * 10.0 ** (-50.0 / 20.0)
+    return x.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(target_seconds, nthreads=0):
+    """Times the oracle port of the path (oracle/pv_ref.c, OpenMP over tracks) on the host cores.
+    Sample: `threads` tracks x 20 s of the cfg-3 signal, repeated until ~target_seconds elapse."""
+    from oracle import oracle as O
+    O.build()
+    threads = nthreads or O.num_threads()
+    sec = 20.0
+    base = vibrato_track_numpy(sec, 1234)
+    x = np.ascontiguousarray(np.tile(base, (threads, 1)))
+    r = semitone_ratio(SEMITONES)
+    F = O.pv_num_frames(x.shape[1], HOP)
+    O.pv_run_batch(x[: max(1, threads // 8)], FFT_N, HOP, r, FS, threads)  # warm-up (page in, spin up OpenMP)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        O.pv_run_batch(x, FFT_N, HOP, r, FS, threads)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= target_seconds or reps >= 50:
+            break
+    return dict(value=threads * F * reps / el, unit="frames/s", cores=threads, kind="port",
+                sample=f"{threads} tracks x {sec:.0f} s (cfg-3 signal, {F} frames each), {reps} passes, "
+                       f"{el:.1f} s wall; double-precision oracle/pv_ref.c, OpenMP over tracks "
+                       f"(FFT engine: in-repo radix-4 double FFT, not FFTW)")
+
+
+def reference_arm(args):
+    """--impl reference: the reference has no phase vocoder and its spec.cpp
+    is a different transform, so the CPU implementation of this metric's path is the oracle port.
+    Each step is one pass over a bounded sample (threads tracks x 20 s)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    threads = O.num_threads()
+    sec = 20.0
+    base = vibrato_track_numpy(sec, 1234)
+    x = np.ascontiguousarray(np.tile(base, (threads, 1)))
+    r = semitone_ratio(SEMITONES)
+    F = O.pv_num_frames(x.shape[1], HOP)
+    for _ in range(min(args.warmup, 2)):
+        O.pv_run_batch(x, FFT_N, HOP, r, FS, threads)
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.pv_run_batch(x, FFT_N, HOP, r, FS, threads)
+    el = time.perf_counter() - t0
+    v = threads * F * steps / el
+    sample = (f"{threads} tracks x {sec:.0f} s per step (cfg-3 signal), {steps} timed steps; oracle/pv_ref.c "
+              f"(double precision, OpenMP over tracks; in-repo FFT, not FFTW)")
+    line = dict(metric=METRIC, value=v, unit="frames/s", n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 2),
+                ms_per_step=1e3 * el / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload="cfg-3 signal, 2048-FFT/512-hop, +3 st, bounded CPU sample", fft=FFT_N, hop=HOP,
+                            semitones=SEMITONES, tracks=threads, seconds=sec),
+                cpu_baseline=dict(value=v, unit="frames/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=0)
+        return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(self.samples), power_w_max=max(self.power) if self.power else None)
+
+
+def gen_tracks_gpu(torch, dev, ntracks, n, rank):
+    """cfg-3 synthetic batch generated on the device (float64 phase, cast to float32):
+    8-harmonic vibrato tone, per-track base 110*2^(t/64*2) Hz, -50 dBFS white noise, seed 1234+track."""
+    x = torch.empty((ntracks, n), dtype=torch.float32, device=dev)
+    t = torch.arange(n, device=dev, dtype=torch.float64) / FS
+    vib = torch.sin(2 * np.pi * 0.5 * t) / 12.0
+    for tr in range(ntracks):
+        gtrack = rank * ntracks + tr
+        f_base = 110.0 * 2.0 ** ((gtrack % 64) / 64.0 * 2.0)
+        f0 = f_base * torch.pow(torch.tensor(2.0, device=dev, dtype=torch.float64), vib)
+        ph = 2 * np.pi * torch.cumsum(f0, 0) / FS
+        s = torch.zeros(n, device=dev, dtype=torch.float64)
+        for h in range(1, 9):
+            s += torch.sin(h * ph) / h
+        s *= 0.5 / s.abs().max()
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + gtrack)
+        s += torch.randn(n, device=dev, dtype=torch.float64, generator=gen) * 10.0 ** (-50.0 / 20.0)
+        x[tr] = s.to(torch.float32)
+        del f0, ph, s
+    return x
+
+
+def load_traffic():
+    """dram bytes per launch from the committed ncu capture (profiles/), if any."""
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import melonix_b200 as m
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nt = args.tracks
+    n = int(round(args.seconds * FS))
+    F = (n + HOP - 1) // HOP
+    frames_per_rank = nt * F
+    rate = semitone_ratio(SEMITONES)
+
+    eng = m.Engine(local)
+    x = gen_tracks_gpu(torch, dev, nt, n, rank)
+    y = torch.empty_like(x)
+    peak = torch.empty((nt, F), dtype=torch.int32, device=dev)
+    f0 = torch.empty((nt, F), dtype=torch.float32, device=dev)
+    eng.use_torch_stream()
+    eng.upload_tracks_dev([x[i] for i in range(nt)])
+    outs = ([y[i] for i in range(nt)], [peak[i] for i in range(nt)], [f0[i] for i in range(nt)])
+
+    def step():
+        eng.pv_run_dev(FFT_N, HOP, rate, outs[0], outs[1], outs[2], sample_rate=FS, wave_mib=args.wave_mib)
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps between CUDA events
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.profile_enable(True)
+    eng.profile_read(reset=True)
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.launch_count - l0
+    prof = eng.profile_read(reset=True)
+    eng.profile_enable(False)
+    ms_per_step = ms_total / args.steps
+    value = world * frames_per_rank / (ms_per_step * 1e-3)
+
+    # ---- roofline of the path's kernels (this rank; per GPU)
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak_gbs, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    kern_ms = {k: v[0] / args.steps for k, v in prof.items() if v[1] > 0}
+    path_ms = sum(kern_ms.values())
+    algo_bytes = ALGO_BYTES_PER_FRAME * frames_per_rank
+    achieved = algo_bytes / (path_ms * 1e-3) / 1e9 if path_ms > 0 else None
+    dom = max(kern_ms, key=kern_ms.get) if kern_ms else None
+    traffic = load_traffic()
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak_gbs, unit="GB/s",
+                    frac=(achieved / peak_gbs) if achieved else None,
+                    traffic=(traffic or {}).get("path_bytes_per_step"),
+                    peak_source=peak_src,
+                    kernel="pv_analyze + pv_scan + pv_synth (the path is three launches per wave)",
+                    algorithmic_bytes_per_frame=ALGO_BYTES_PER_FRAME, frames_per_step=frames_per_rank,
+                    kernel_ms_per_step=kern_ms, dominant=dom,
+                    kernel_share={k: v / path_ms for k, v in kern_ms.items()} if path_ms else None,
+                    launches_per_step={k: v[1] / args.steps for k, v in prof.items() if v[1] > 0})
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host in/out, copies timed)
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((nt, n), dtype=torch.float32, pin_memory=True)
+        hx.copy_(x)
+        hy = torch.empty((nt, n), dtype=torch.float32, pin_memory=True)
+        hp = torch.empty((nt, F), dtype=torch.int32, pin_memory=True)
+        hf = torch.empty((nt, F), dtype=torch.float32, pin_memory=True)
+        del x, y
+        torch.cuda.empty_cache()
+        ins = [hx[i] for i in range(nt)]
+        ho = ([hy[i] for i in range(nt)], [hp[i] for i in range(nt)], [hf[i] for i in range(nt)])
+
+        def estep():
+            eng.pv_process_host(ins, FFT_N, HOP, rate, ho[0], ho[1], ho[2], sample_rate=FS, wave_mib=args.wave_mib)
+
+        estep()  # warm-up (allocations)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            estep()
+        barrier()
+        el = max_over_ranks(time.perf_counter() - t0)
+        e2e = dict(value=world * frames_per_rank * args.e2e_steps / el, unit="frames/s",
+                   h2d_bytes_per_step=int(nt * n * 4), d2h_bytes_per_step=int(nt * n * 4 + nt * F * 8),
+                   ms_per_step=1e3 * el / args.e2e_steps, steps=args.e2e_steps,
+                   api="mlx_pv_process_host (C ABI; pinned host buffers; H2D/D2H on copy streams overlapped "
+                       "with the kernels per track)")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.cpu_seconds)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload="BASELINE configs[2]: 64 mono tracks x 5 min per GPU, 2048-FFT/512-hop, "
+                                         "pitch detect + shift +3 st (tracks shard across GPUs, no collective)",
+                                tracks_per_gpu=nt, seconds_per_track=args.seconds, fft=FFT_N, hop=HOP,
+                                semitones=SEMITONES, sample_rate=FS, frames_per_gpu=frames_per_rank,
+                                analysis_fft="f64", synthesis_fft="f32", phase_accumulator="u32",
+                                wave_mib=args.wave_mib,
+                                l2="inputs and outputs (3.7 GB each per GPU) exceed the 126 MB L2; no flush needed"),
+                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,6 +54,13 @@ MLX_API int mlx_device_info(mlx_ctx *ctx, int *sm_count, int *cc, size_t *total_
 /* number of kernels launched by this context since creation (bench.py's gpu_launches). */
 MLX_API int64_t mlx_launch_count(const mlx_ctx *ctx);
 
+/* Per-kernel device timing with CUDA events on the context stream (what bench.py's roofline
+ * object is computed from).  kinds: 0 = pv_analyze, 1 = pv_scan, 2 = pv_synth, 3 = spec, 4 = grain.
+ * mlx_profile_read synchronises the stream, adds up the time between consecutive launch marks per
+ * kind into ms[5] / launches[5], and clears the marks when reset != 0. */
+MLX_API int mlx_profile_enable(mlx_ctx *ctx, int on);
+MLX_API int mlx_profile_read(mlx_ctx *ctx, double *ms, int64_t *launches, int reset);
+
 /* ---- tracks ------------------------------------------------------------------------------- */
 /* Replaces Spec::Spec(std::span<float> wav) (reference spec.cpp:10-16): the reference keeps a
  * non-owning view of the mono track; here the samples are copied once into HBM, zero-padded on

@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
     L.mlx_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_size_t)]
     L.mlx_launch_count.argtypes = [vp]
     L.mlx_launch_count.restype = i64
+    L.mlx_profile_enable.argtypes = [vp, i32]
+    L.mlx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), i32]
     L.mlx_upload_tracks.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32]
     L.mlx_upload_tracks_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i32]
     L.mlx_num_tracks.argtypes = [vp]

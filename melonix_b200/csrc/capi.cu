@@ -55,7 +55,7 @@ struct DevBuf {
 };
 
 struct Tables {
-  DevBuf tw_d, twr_d, tw_f, twr_f, win, wsyn;
+  DevBuf tw_d, twr_d, tw_f, twr_f, win, win_d, wsyn;
   bool pv_ready = false, spec_ready = false;
 };
 
@@ -74,13 +74,28 @@ struct mlx_ctx {
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of mlx_pv_process_host
   int64_t launches = 0;
 
+  // optional per-kernel timing: one event before every launch, one after the last of a sequence
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_kind;  // kind of the launch that follows mark i; -1 = end of sequence
+  void mark(int kind) {
+    if (!profiling) return;
+    if (ev_kind.size() == ev_pool.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      ev_pool.push_back(e);
+    }
+    cudaEventRecord(ev_pool[ev_kind.size()], stream);
+    ev_kind.push_back(kind);
+  }
+
   DevBuf track_buf;
   std::vector<Track> tracks;
 
   std::map<int, Tables> tables;
 
   // phase-vocoder scratch
-  DevBuf smag, lacc, tot, pre, carry, track_desc, ptr_stage;
+  DevBuf smag, lacc, tot, pre, carry, track_desc, ptr_stage, gk;
   DevBuf out_wav, out_peak, out_f0;  // device results for the host-pointer entry points
   DevBuf jobs, spec_out, spec_rgb;
   DevBuf g_i32a, g_i32b, g_f32a, g_f32b, g_i64, g_out, g_out16;
@@ -144,9 +159,11 @@ int ensure_tables(mlx_ctx* c, int N, bool want_pv, Tables** out) {
     }
     // PV-spec A.1: periodic Hann computed in double, stored as float; A.7: g = H / sum w^2 (float)
     std::vector<float> win(N), wsyn(N);
+    std::vector<double> wind(N);
     double sw2 = 0.0;
     for (int j = 0; j < N; ++j) {
       win[j] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)j / (double)N));
+      wind[j] = (double)win[j];
       sw2 += (double)win[j] * (double)win[j];
     }
     const float g = (float)((double)(N / 4) / sw2);
@@ -155,6 +172,7 @@ int ensure_tables(mlx_ctx* c, int N, bool want_pv, Tables** out) {
     if ((rc = upload_vec(tb.tw_d, twd, c->stream))) return rc;
     if ((rc = upload_vec(tb.twr_d, twrd, c->stream))) return rc;
     if ((rc = upload_vec(tb.win, win, c->stream))) return rc;
+    if ((rc = upload_vec(tb.win_d, wind, c->stream))) return rc;
     if ((rc = upload_vec(tb.wsyn, wsyn, c->stream))) return rc;
     CK(pv_configure(N));
     tb.pv_ready = true;
@@ -278,10 +296,35 @@ int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth,
 
   PvTables pt{static_cast<const cplx<double>*>(tb->tw_d.p), static_cast<const cplx<double>*>(tb->twr_d.p),
               static_cast<const cplx<float>*>(tb->tw_f.p),  static_cast<const cplx<float>*>(tb->twr_f.p),
-              static_cast<const float*>(tb->win.p),         static_cast<const float*>(tb->wsyn.p)};
+              static_cast<const float*>(tb->win.p),         static_cast<const double*>(tb->win_d.p),
+              static_cast<const float*>(tb->wsyn.p)};
   PvScratch sc{static_cast<float*>(c->smag.p), static_cast<uint32_t*>(c->lacc.p), static_cast<uint32_t*>(c->tot.p),
                static_cast<uint32_t*>(c->pre.p), static_cast<uint32_t*>(c->carry.p)};
   const PvTrack* tdev = static_cast<const PvTrack*>(c->track_desc.p);
+
+  // bin-shift table for the constant rate (PV-spec A.5): one float multiply per bin, as the spec says
+  {
+    const int NC = pl.N / 2, NB = NC + 1;
+    std::vector<uint32_t> gk(pl.NBP, 1u);
+    std::vector<int> klo(NB, 1), khi(NB, 0);
+    const float r = p->rate;
+    for (int k = 0; k < NB; ++k) {
+      const float tf = (float)k * r;  // one float multiply, as the spec says
+      const int j = (int)std::trunc(tf);
+      if (j < 0 || j >= NB) continue;
+      if (klo[j] > khi[j]) klo[j] = k;
+      khi[j] = k;
+    }
+    for (int j = 0; j < NB; ++j) {
+      if (klo[j] <= khi[j]) {
+        gk[j] = (uint32_t)klo[j] | ((uint32_t)khi[j] << 16);
+      } else {
+        gk[j] = 1u;
+      }
+    }
+    CK(c->gk.reserve(sizeof(uint32_t) * pl.NBP));
+    CK(cudaMemcpyAsync(c->gk.p, gk.data(), sizeof(uint32_t) * pl.NBP, cudaMemcpyHostToDevice, c->stream));
+  }
 
   int kmin = (int)std::ceil(50.0 * pl.N / p->sample_rate), kmax = (int)std::floor(2000.0 * pl.N / p->sample_rate);
   kmin = std::max(kmin, 1);
@@ -301,14 +344,20 @@ int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth,
     wv.fs_over_N = (float)(p->sample_rate / (double)pl.N);
     wv.kmin = kmin;
     wv.kmax = kmax;
+    wv.gk = static_cast<const uint32_t*>(c->gk.p);
+    wv.r_fix = (long long)((double)p->rate * 67108864.0);
+    c->mark(0);
     CK(launch_pv_analyze(pl.N, tdev, nt, wv, pt, sc, c->stream));
+    c->mark(1);
     CK(launch_pv_scan(pl.N, nt, wv, sc, c->stream));
     c->launches += 2;
     if (synth) {
+      c->mark(2);
       CK(launch_pv_synth(pl.N, tdev, nt, wv, pt, sc, c->stream));
       c->launches += 1;
     }
   }
+  c->mark(-1);
   if (totals_dev) {
     for (int t = 0; t < nt; ++t)
       if (totals_dev[t])
@@ -356,14 +405,15 @@ void mlx_destroy(mlx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&c->track_buf, &c->smag, &c->lacc, &c->tot, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
+  for (DevBuf* b : {&c->gk, &c->track_buf, &c->smag, &c->lacc, &c->tot, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
                     &c->out_wav, &c->out_peak, &c->out_f0, &c->jobs, &c->spec_out, &c->spec_rgb, &c->g_i32a,
                     &c->g_i32b, &c->g_f32a, &c->g_f32b, &c->g_i64, &c->g_out, &c->g_out16})
     b->release();
   for (auto& kv : c->tables)
     for (DevBuf* b : {&kv.second.tw_d, &kv.second.twr_d, &kv.second.tw_f, &kv.second.twr_f, &kv.second.win,
-                      &kv.second.wsyn})
+                      &kv.second.win_d, &kv.second.wsyn})
       b->release();
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -392,6 +442,32 @@ int mlx_device_info(mlx_ctx* c, int* sm_count, int* cc, size_t* total_mem) {
 }
 
 int64_t mlx_launch_count(const mlx_ctx* c) { return c ? c->launches : 0; }
+
+int mlx_profile_enable(mlx_ctx* c, int on) {
+  if (!c) return fail(MLX_ERR_INVALID, "ctx is null");
+  c->profiling = on != 0;
+  return MLX_OK;
+}
+
+int mlx_profile_read(mlx_ctx* c, double* ms, int64_t* launches, int reset) {
+  if (!c || !ms || !launches) return fail(MLX_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 5; ++k) {
+    ms[k] = 0.0;
+    launches[k] = 0;
+  }
+  for (size_t i = 0; i + 1 < c->ev_kind.size(); ++i) {
+    const int kind = c->ev_kind[i];
+    if (kind < 0 || kind >= 5) continue;
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, c->ev_pool[i], c->ev_pool[i + 1]));
+    ms[kind] += t;
+    launches[kind] += 1;
+  }
+  if (reset) c->ev_kind.clear();
+  return MLX_OK;
+}
 
 int mlx_upload_tracks(mlx_ctx* c, const float* const* wav, const int64_t* n, int ntracks) {
   if (!c || !wav) return fail(MLX_ERR_INVALID, "null argument");
@@ -447,7 +523,9 @@ static int spec_common(mlx_ctx* c, int track, int fftN, const int* jobs_dev, int
   a.kcol = k;
   a.tw_f = static_cast<const cplx<float>*>(tb->tw_f.p);
   a.twr_f = static_cast<const cplx<float>*>(tb->twr_f.p);
+  c->mark(3);
   CK(launch_spec(fftN, a, c->stream));
+  c->mark(-1);
   if (count > 0) c->launches += 1;
   return MLX_OK;
 }
@@ -679,7 +757,9 @@ int mlx_grain_render(mlx_ctx* c, int track, const int32_t* g_start, const int32_
   a.total = total;
   a.out = out ? static_cast<float*>(c->g_out.p) : nullptr;
   a.out_i16 = out_i16 ? static_cast<short*>(c->g_out16.p) : nullptr;
+  c->mark(4);
   CK(launch_grain(a, c->stream));
+  c->mark(-1);
   c->launches += 1;
   if (out) CK(cudaMemcpyAsync(out, c->g_out.p, sizeof(float) * total, cudaMemcpyDeviceToHost, c->stream));
   if (out_i16)

@@ -30,6 +30,7 @@ struct PvTables {
   const cplx<float>* tw_f;
   const cplx<float>* twr_f;
   const float* win;           // periodic Hann, float, [fftN]
+  const double* win_d;        // the same float values widened to double (exact), [fftN]
   const float* wsyn;          // gain * win / fftN  (synthesis window incl. irfft 1/N), [fftN]
 };
 
@@ -43,6 +44,10 @@ struct PvWave {
   float rate;
   float fs_over_N;
   int kmin, kmax;
+  // bin-shift table for the constant `rate` (PV-spec A.5), built on the host per call:
+  //   gk[j] = klo | khi << 16 with K_j = [klo, khi] (klo = 1, khi = 0 when empty)
+  const uint32_t* gk;
+  long long r_fix;  // rate * 2^26, exact (a float has 24 significant bits)
 };
 
 struct PvScratch {

@@ -39,10 +39,11 @@ struct PvCfg {
   static constexpr int THREADS = G * TPF;
   static constexpr int BUF = FftPlan<NC>::BUF;
   static constexpr int TILE = N + (G - 1) * H;  // floats per batch tile
-  static constexpr int QP = (NC / 2 + 1 + THREADS - 1) / THREADS;  // pair slots per thread
+  static constexpr int QP = (NC / 2 + THREADS - 1) / THREADS;      // pair slots per thread (k = 1..NC/2)
   static constexpr int QB = (NB + THREADS - 1) / THREADS;          // bin slots per thread
-  static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUF + sizeof(float) * TILE +
-                                   sizeof(float) * 2 * G * NBP + 64;
+  static constexpr bool WIN_D = (N <= 4096);                       // double window staged in smem
+  static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUF + (WIN_D ? sizeof(double) * N : 0) +
+                                   sizeof(float) * 2 * TILE + sizeof(float) * 2 * G * NBP + 64;
   static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + sizeof(float) * 2 * 3 * H + 64;
 };
 
@@ -105,22 +106,117 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// ------------------------------------------------------------------------------------------------
+// scalar helpers shared by K_A / K_S
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// |atan2(y, x)| in [0, pi] from |y| and signed x.  atan(t) = t * P(t^2) on [0,1] (degree-8 fit,
+// 1.1e-7 rad max error evaluated in float), one MUFU.RCP, no branches, no slow paths.
+__device__ __forceinline__ float atan2_abs(float ay, float x) {
+  const float ax = fabsf(x);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = mn * fast_rcp(mx);
+  const float s = t * t;
+  float p = 2.834064187e-03f;
+  p = fmaf(p, s, -1.600502990e-02f);
+  p = fmaf(p, s, 4.258760810e-02f);
+  p = fmaf(p, s, -7.495445758e-02f);
+  p = fmaf(p, s, 1.063675433e-01f);
+  p = fmaf(p, s, -1.420257092e-01f);
+  p = fmaf(p, s, 1.999248415e-01f);
+  p = fmaf(p, s, -3.333306611e-01f);
+  p = fmaf(p, s, 1.0f);
+  p *= t;
+  p = (ay > ax) ? 1.5707963267948966f - p : p;
+  p = (x < 0.f) ? 3.1415926535897931f - p : p;
+  return p;
+}
+
+// One analysis bin (PV-spec A.2-A.3).  X = (a, b) this frame and (c, d) previous frame in double.
+//
+// The frame's absolute phase is quantised to integer turns P = round(arg(X) / 2pi * 2^32) (float
+// atan2 polynomial: its smooth error e(phi) enters the phase *difference* as e(phi_f) - e(phi_{f-1})
+// and therefore telescopes over frames instead of accumulating), and
+//     d = P_f - P_{f-1} - bin * 2^30   (mod 2^32, as a signed 32-bit number)
+// is exact integer arithmetic.  The only discontinuous decision -- on which side of the +-pi cut d
+// lies -- is taken from the sign of Im(X conj(Xprev) (-i)^bin) evaluated in DOUBLE; when the
+// integer difference landed on the other side, `flip` tells the consumer to add -+2^32.
+__device__ __forceinline__ void analysis_bin(double a, double b, double c, double d, uint32_t& p_prev,
+                                             float& mag_prev, int bin, bool real_bin, float& mag, int& d32,
+                                             bool& flip) {
+  const float af = (float)a, bf = (float)b;
+  mag = fast_sqrt(fmaf(af, af, bf * bf));
+  const float pabs = atan2_abs(fabsf(bf), af);
+  uint32_t P = __float2uint_rn(pabs * 683565275.5764316f);  // 2^32 / (2 pi); pabs <= pi -> <= 2^31
+  P = (__float_as_uint(bf) >> 31) ? (0u - P) : P;
+  d32 = (int)(P - p_prev - ((uint32_t)bin << 30));
+  // the double component that ends up as Im Z: odd bins -> -(ac + bd), even bins -> (bc - ad)
+  const bool odd = bin & 1, neg = bin & 2;
+  const double u = odd ? a : b, v = odd ? b : -a;
+  const double s64 = fma(u, c, v * d);
+  unsigned sbit = ((unsigned)__double2hiint(s64) >> 31) ^ (odd ? 1u : 0u) ^ (neg ? 1u : 0u);
+  if (real_bin) sbit = 0u;  // bins 0 and N/2 are purely real: Im Z := +0, d in {0, +pi}
+  const bool gate = mag * mag_prev <= 1e-18f;  // silence gate |Z| <= 1e-18 -> d = 0
+  const unsigned dneg = (unsigned)d32 >> 31;
+  const unsigned dabs = dneg ? (0u - (unsigned)d32) : (unsigned)d32;
+  flip = !gate && dabs > 0x40000000u && dneg != sbit;
+  d32 = gate ? 0 : d32;
+  p_prev = P;
+  mag_prev = mag;
+}
+
 // trunc(float(k) * r) with a plain float multiply, exactly as the spec (A.5) and the oracle do.
 __device__ __forceinline__ int shift_bin(int k, float r) { return (int)truncf(__fmul_rn((float)k, r)); }
 
-// K_j = { k in [0, NC] : shift_bin(k, r) == j };  returns klo > khi when empty.
-__device__ __forceinline__ void gather_range(int j, float r, int NC, int& klo, int& khi) {
+// Slow path for per-frame rates: K_j = { k in [0, NC] : shift_bin(k, r) == j } searched on the
+// device (klo > khi when empty) plus the base increment.  The constant-rate path reads tables.
+__device__ __noinline__ void gather_entry_slow(int j, float r, int NC, uint32_t& kk) {
   int k = (int)(__fdividef((float)j, r)) - 1;
   k = max(0, min(k, NC));
   while (k <= NC && shift_bin(k, r) < j) ++k;
   while (k > 0 && shift_bin(k - 1, r) >= j) --k;
-  klo = k;
   if (k > NC || shift_bin(k, r) != j) {
-    khi = k - 1;
+    kk = 1u;  // klo = 1, khi = 0
     return;
   }
-  khi = k;
+  int khi = k;
   while (khi + 1 <= NC && shift_bin(khi + 1, r) == j) ++khi;
+  kk = (uint32_t)k | ((uint32_t)khi << 16);
+}
+
+// sin/cos of 2*pi*acc/2^32: the quadrant comes from the top bits (exact range reduction for free),
+// the remainder phi in [-pi/4, pi/4) goes through degree-7/8 polynomials (6e-8 max error in float).
+__device__ __forceinline__ void sincos_turns(uint32_t acc, float& s, float& c) {
+  const uint32_t k = (acc + 0x20000000u) >> 30;
+  const int f = (int)(acc - (k << 30));  // [-2^29, 2^29)
+  // (f >> 7) as float without an I2F: exponent trick, exact for |.| < 2^22
+  const float fq = __int_as_float(0x4B400000 + (f >> 7)) - 12582912.0f;
+  const float phi = fq * 1.8725351414619643e-07f;  // 2 pi * 2^7 / 2^32
+  const float s2 = phi * phi;
+  float sp = -1.950396254e-04f;
+  sp = fmaf(sp, s2, 8.332036436e-03f);
+  sp = fmaf(sp, s2, -1.666665077e-01f);
+  sp = fmaf(sp, s2, 1.0f);
+  sp *= phi;
+  float cp = 2.437988041e-05f;
+  cp = fmaf(cp, s2, -1.388661913e-03f);
+  cp = fmaf(cp, s2, 4.166661575e-02f);
+  cp = fmaf(cp, s2, -0.5f);
+  cp = fmaf(cp, s2, 1.0f);
+  const bool sw = k & 1u;
+  float ss = sw ? cp : sp, cc = sw ? sp : cp;
+  s = (k & 2u) ? -ss : ss;
+  c = ((k + 1u) & 2u) ? -cc : cc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -131,15 +227,17 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   using Cfg = PvCfg<N, G>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NB = Cfg::NB, NBP = Cfg::NBP;
   constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUF, TILE = Cfg::TILE, QP = Cfg::QP, QB = Cfg::QB;
+  constexpr bool WD = Cfg::WIN_D;
   using C = cplx<double>;
   using F = Fft<double, NC, -1>;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  C* buf = reinterpret_cast<C*>(smem_raw);                       // [G][BUF]
-  float* tile = reinterpret_cast<float*>(buf + G * BUF);         // [TILE]
-  float* s_mag = tile + TILE;                                    // [G][NBP]
-  float* s_del = s_mag + G * NBP;                                // [G][NBP]  d / (2 pi), turns
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_del + G * NBP); // 8-byte aligned (all sizes even)
+  C* buf = reinterpret_cast<C*>(smem_raw);                        // [G][BUF]
+  double* s_win = reinterpret_cast<double*>(buf + G * BUF);       // [N] when WD
+  float* tile = reinterpret_cast<float*>(s_win + (WD ? N : 0));   // [2][TILE]
+  float* s_mag = tile + 2 * TILE;                                 // [G][NBP]
+  int* s_del = reinterpret_cast<int*>(s_mag + G * NBP);           // [G][NBP]  d/(2 pi) * 2^32 (wrapped)
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_del + G * NBP);  // [2]
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
@@ -152,57 +250,72 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     return;
   }
   const long long b = min(a + (long long)wv.CA, lim);
+  const int nbatch = (int)((b - a + 1 + G - 1) / G);  // frames a-1 .. b-1
 
-  if (tid == 0) mbar_init(mbar, 1);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar + 1, 1);
+  }
+  if constexpr (WD) {
+    for (int i = tid; i < N; i += THREADS) s_win[i] = tb.win_d[i];
+  }
+  __syncthreads();  // mbarriers initialised, window staged
+  if (tid == 0) {   // first tile: samples [(a-1-3)H, (a-1+G)H) of the zero-padded track
+    mbar_expect_tx(mbar, TILE * sizeof(float));
+    tma_load_1d(tile, tr.x + (a - 4) * H, TILE * sizeof(float), mbar);
+  }
 
   FftTwiddles<double, NC, -1> twd;
   twd.init(t, tb.tw_d);
-  float wreg[32];
-#pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    const float2 w2 = *reinterpret_cast<const float2*>(tb.win + 2 * (t + m * TPF));
-    wreg[2 * m] = w2.x;
-    wreg[2 * m + 1] = w2.y;
-  }
-  // pair slots: bins k and NC-k, k = tid + q*THREADS in [0, NC/2]
-  C wr[QP], pk[QP], pm[QP];
+  // pair slots: bins k and NC-k for k = 1 + tid + q*THREADS <= NC/2; thread 0 also owns (0, NC)
+  // previous frame per bin: X (double, for the cut decision), integer phase, magnitude.
+  // Frame -1 has phi = 0 <=> X = 1.
+  C pk[QP], pm[QP];
+  uint32_t ppk[QP], ppm[QP];
+  float pmk[QP], pmm[QP];
 #pragma unroll
   for (int q = 0; q < QP; ++q) {
-    const int k = tid + q * THREADS;
-    wr[q] = (k <= NC / 2) ? tb.twr_d[k] : C{1.0, 0.0};
-    pk[q] = C{1.0, 0.0};
-    pm[q] = C{1.0, 0.0};
+    pk[q] = pm[q] = C{1.0, 0.0};
+    ppk[q] = ppm[q] = 0u;
+    pmk[q] = pmm[q] = 1.f;
   }
+  double p0 = 1.0, pn = 1.0;  // previous X[0], X[NC] (real)
+  uint32_t pp0 = 0u, ppn = 0u;
+  float pm0 = 1.f, pmn = 1.f;
   uint32_t lacc[QB], tot[QB];
 #pragma unroll
   for (int q = 0; q < QB; ++q) lacc[q] = tot[q] = 0u;
-
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
-  __syncthreads();  // mbarrier initialised
-
-  const int nbatch = (int)((b - a + 1 + G - 1) / G);  // frames a-1 .. b-1
   const size_t row0 = (size_t)blockIdx.y * wv.rows;
-  uint32_t parity = 0;
+  const bool per_frame_rate = tr.rate_pf != nullptr;
 
   for (int bi = 0; bi < nbatch; ++bi) {
     const long long f_first = a - 1 + (long long)bi * G;
-    // ---- TMA: samples [(f_first-3)H, (f_first+G)H) of the zero-padded track
-    if (tid == 0) {
-      mbar_expect_tx(mbar, TILE * sizeof(float));
-      tma_load_1d(tile, tr.x + (f_first - 3) * H, TILE * sizeof(float), mbar);
+    float* cur = tile + (bi & 1) * TILE;
+    // ---- TMA: prefetch the next batch's tile, then wait for this one
+    if (tid == 0 && bi + 1 < nbatch) {
+      mbar_expect_tx(mbar + ((bi + 1) & 1), TILE * sizeof(float));
+      tma_load_1d(tile + ((bi + 1) & 1) * TILE, tr.x + (f_first + G - 3) * H, TILE * sizeof(float),
+                  mbar + ((bi + 1) & 1));
     }
-    mbar_wait(mbar, parity);
-    parity ^= 1u;
+    mbar_wait(mbar + (bi & 1), (bi >> 1) & 1);
 
     // ---- forward FP64 real FFT of frame f_first + g (N/2-point complex on even/odd samples)
     const long long fg = f_first + g;
     if (fg >= 0 && fg < b) {
       C x[16];
-      const float* src = tile + g * H;
+      const float* src = cur + g * H;
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
-        const float2 s2 = *reinterpret_cast<const float2*>(src + 2 * (t + m * TPF));
-        x[m] = C{(double)wreg[2 * m] * (double)s2.x, (double)wreg[2 * m + 1] * (double)s2.y};
+        const int i = t + m * TPF;
+        const float2 s2 = *reinterpret_cast<const float2*>(src + 2 * i);
+        if constexpr (WD) {
+          const double2 w2 = *reinterpret_cast<const double2*>(s_win + 2 * i);
+          x[m] = C{w2.x * (double)s2.x, w2.y * (double)s2.y};
+        } else {
+          const float2 w2 = __ldg(reinterpret_cast<const float2*>(tb.win + 2 * i));
+          x[m] = C{(double)w2.x * (double)s2.x, (double)w2.y * (double)s2.y};
+        }
       }
       F::run(x, buf + g * BUF, t, twd, bar);
       F::store(x, buf + g * BUF, t);  // same thread-private slots as the in-place last stage
@@ -214,61 +327,59 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     for (int gg = 0; gg < G; ++gg) {
       const long long ff = f_first + gg;
       if (ff >= b) break;
-      if (ff < 0) continue;  // frame -1: phi = 0 <=> X = 1 (initial pk/pm)
+      if (ff < 0) continue;  // frame -1: phi = 0 <=> X = 1 (initial values)
       const C* zb = buf + gg * BUF;
+      const bool emit = (bi != 0 || gg != 0);  // the chunk's leading halo frame only seeds "previous"
+      float* mg = s_mag + gg * NBP;
+      int* dl = s_del + gg * NBP;
 #pragma unroll
       for (int q = 0; q < QP; ++q) {
-        const int k = tid + q * THREADS;
-        if (k > NC / 2) continue;
-        const int mbin = NC - k;
-        const C za = zb[fft_pad(k)];
-        const C zc = zb[fft_pad(mbin & (NC - 1))];
-        C xk, xm;
-        if (k == 0) {
-          xk = C{za.x + za.y, 0.0};
-          xm = C{za.x - za.y, 0.0};
-        } else {
+        const int k = 1 + tid + q * THREADS;
+        if (k <= NC / 2) {
+          const int mbin = NC - k;
+          const C za = zb[fft_pad(k)];
+          const C zc = zb[fft_pad(mbin)];
+          const C w = tb.twr_d[k];
           const double er = 0.5 * (za.x + zc.x), ei = 0.5 * (za.y - zc.y);
           const double dr = 0.5 * (za.x - zc.x), di = 0.5 * (za.y + zc.y);
-          const double tr_ = dr * wr[q].x - di * wr[q].y, ti_ = dr * wr[q].y + di * wr[q].x;
-          xk = C{er + ti_, ei - tr_};
-          xm = C{er - ti_, -ei - tr_};
-        }
-        if (bi != 0 || gg != 0) {  // the chunk's leading halo frame only seeds pk/pm
-          // Z = X conj(Xprev) (-i)^bin ; real bins (0 and NC) have Im Z := +0
-          {
-            double zr = xk.x * pk[q].x + xk.y * pk[q].y, zi = xk.y * pk[q].x - xk.x * pk[q].y;
-            double rr, ri;
-            switch (k & 3) {
-              case 1: rr = zi; ri = -zr; break;
-              case 2: rr = -zr; ri = -zi; break;
-              case 3: rr = -zi; ri = zr; break;
-              default: rr = zr; ri = zi; break;
-            }
-            if (k == 0) ri = 0.0;
-            const float d = (rr * rr + ri * ri <= 1e-36) ? 0.f : atan2f((float)ri, (float)rr);
-            const float ax = (float)xk.x, ay = (float)xk.y;
-            s_mag[gg * NBP + k] = sqrtf(ax * ax + ay * ay);
-            s_del[gg * NBP + k] = d * 0.15915494309189535f;
+          const double tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
+          const C xk{er + ti_, ei - tr_};
+          const C xm{er - ti_, -ei - tr_};
+          float mag;
+          int dq;
+          bool flip;
+          analysis_bin(xk.x, xk.y, pk[q].x, pk[q].y, ppk[q], pmk[q], k, false, mag, dq, flip);
+          if (emit) {
+            mg[k] = flip ? -mag : mag;  // sign bit of the stored magnitude carries `flip`
+            dl[k] = dq;
           }
-          {
-            double zr = xm.x * pm[q].x + xm.y * pm[q].y, zi = xm.y * pm[q].x - xm.x * pm[q].y;
-            double rr, ri;
-            switch (mbin & 3) {
-              case 1: rr = zi; ri = -zr; break;
-              case 2: rr = -zr; ri = -zi; break;
-              case 3: rr = -zi; ri = zr; break;
-              default: rr = zr; ri = zi; break;
-            }
-            if (k == 0) ri = 0.0;
-            const float d = (rr * rr + ri * ri <= 1e-36) ? 0.f : atan2f((float)ri, (float)rr);
-            const float ax = (float)xm.x, ay = (float)xm.y;
-            s_mag[gg * NBP + mbin] = sqrtf(ax * ax + ay * ay);
-            s_del[gg * NBP + mbin] = d * 0.15915494309189535f;
+          analysis_bin(xm.x, xm.y, pm[q].x, pm[q].y, ppm[q], pmm[q], mbin, false, mag, dq, flip);
+          if (emit) {
+            mg[mbin] = flip ? -mag : mag;
+            dl[mbin] = dq;
           }
+          pk[q] = xk;
+          pm[q] = xm;
         }
-        pk[q] = xk;
-        pm[q] = xm;
+      }
+      if (tid == 0) {  // DC and Nyquist are real: X[0] = Re Z0 + Im Z0, X[NC] = Re Z0 - Im Z0
+        const C z0 = zb[0];
+        const double x0 = z0.x + z0.y, xn = z0.x - z0.y;
+        float mag;
+        int dq;
+        bool flip;
+        analysis_bin(x0, 0.0, p0, 0.0, pp0, pm0, 0, true, mag, dq, flip);
+        if (emit) {
+          mg[0] = flip ? -mag : mag;
+          dl[0] = dq;
+        }
+        analysis_bin(xn, 0.0, pn, 0.0, ppn, pmn, NC, true, mag, dq, flip);
+        if (emit) {
+          mg[NC] = flip ? -mag : mag;
+          dl[NC] = dq;
+        }
+        p0 = x0;
+        pn = xn;
       }
     }
     __syncthreads();
@@ -278,31 +389,44 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     for (int gg = (bi == 0 ? 1 : 0); gg < G; ++gg) {
       const long long ff = f_first + gg;
       if (ff >= b) break;
-      const float r = tr.rate_pf ? tr.rate_pf[ff] : wv.rate;
       const float* mg = s_mag + gg * NBP;
-      const float* dl = s_del + gg * NBP;
+      const int* dl = s_del + gg * NBP;
       const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
+      float r = wv.rate;
+      unsigned long long r_fix = (unsigned long long)wv.r_fix;
+      if (per_frame_rate) {
+        r = tr.rate_pf[ff];
+        r_fix = (unsigned long long)((double)r * 67108864.0);
+      }
+      const bool counted = ff < wv.we;
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
         const int j = tid + q * THREADS;
-        if (j >= NB) continue;
-        int klo, khi;
-        gather_range(j, r, NC, klo, khi);
-        float smag = 0.f;
-        uint32_t inc;
-        if (klo <= khi) {
-          for (int k = klo; k <= khi; ++k) smag += mg[k];
-          // frac(r * nu / osamp) = frac(r * (khi/4 + d/(2 pi))), evaluated in double
-          double tt = (double)r * (0.25 * (double)khi + (double)dl[khi]);
-          tt -= floor(tt);
-          inc = (uint32_t)(unsigned long long)__double2ll_rn(tt * 4294967296.0);
-        } else {
-          inc = ((uint32_t)j & 3u) << 30;  // s_nu = j  ->  frac(j/4)
+        if (j < NB) {
+          uint32_t kk;
+          if (per_frame_rate) {
+            gather_entry_slow(j, r, NC, kk);
+          } else {
+            kk = __ldg(wv.gk + j);
+          }
+          const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
+          float smag = 0.f;
+          uint32_t inc = ((uint32_t)j & 3u) << 30;  // empty K_j: s_nu = j -> frac(j / 4)
+          if (klo <= khi) {
+            for (int k = klo; k <= khi; ++k) smag += fabsf(mg[k]);
+            // frac(rate * nu / 4) * 2^32 with nu/4 = (khi * 2^30 + d) / 2^32 turns, d the signed
+            // phase advance (+-2^32 when the cut decision says so): one exact 64-bit product mod 2^64,
+            // rounded once -- the same single rounding per frame as the oracle's llrint.
+            long long dd = (long long)dl[khi];
+            if (__float_as_uint(mg[khi]) >> 31) dd += (dd < 0) ? 4294967296LL : -4294967296LL;
+            const unsigned long long nu = (unsigned long long)(((long long)khi << 30) + dd);
+            inc = (uint32_t)((r_fix * nu + (1ULL << 25)) >> 26);
+          }
+          lacc[q] += inc;
+          if (counted) tot[q] = lacc[q];
+          sc.smag[row + j] = smag;
+          sc.lacc[row + j] = lacc[q];
         }
-        lacc[q] += inc;
-        if (ff < wv.we) tot[q] = lacc[q];
-        sc.smag[row + j] = smag;
-        sc.lacc[row + j] = lacc[q];
       }
     }
 
@@ -316,7 +440,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         float best = -1.f;
         int bk = wv.kmin;
         for (int k = wv.kmin + lane; k <= wv.kmax; k += 32) {
-          const float v = mg[k];
+          const float v = fabsf(mg[k]);
           if (v > best) { best = v; bk = k; }
         }
 #pragma unroll
@@ -327,7 +451,11 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         }
         if (lane == 0) {
           if (tr.peak) tr.peak[ff] = bk;
-          if (tr.f0) tr.f0[ff] = ((float)bk + 4.f * s_del[gg * NBP + bk]) * wv.fs_over_N;
+          if (tr.f0) {
+            long long dd = (long long)s_del[gg * NBP + bk];
+            if (__float_as_uint(mg[bk]) >> 31) dd += (dd < 0) ? 4294967296LL : -4294967296LL;
+            tr.f0[ff] = ((float)bk + (float)dd * 9.313225746154785e-10f) * wv.fs_over_N;  // nu = k + 4 d
+          }
         }
       }
     }
@@ -364,12 +492,13 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   using Cfg = PvCfg<N, G>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NBP = Cfg::NBP;
   constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUF, QP = Cfg::QP;
+  constexpr int H2 = H / 2;
   using C = cplx<float>;
   using F = Fft<float, NC, +1>;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  C* buf = reinterpret_cast<C*>(smem_raw);                 // [G][BUF]
-  float* carry = reinterpret_cast<float*>(buf + G * BUF);  // [2][3][H]
+  C* buf = reinterpret_cast<C*>(smem_raw);                   // [G][BUF]
+  float2* carry = reinterpret_cast<float2*>(buf + G * BUF);  // [2][3][H/2]
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
@@ -394,54 +523,69 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   uint32_t prek[QP], prem[QP];
 #pragma unroll
   for (int q = 0; q < QP; ++q) {
-    const int k = tid + q * THREADS;
+    const int k = 1 + tid + q * THREADS;
     wr[q] = (k <= NC / 2) ? tb.twr_f[k] : C{1.f, 0.f};
     prek[q] = prem[q] = 0u;
   }
+  uint32_t pre0 = 0u, pren = 0u;
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
 
   const int nbatch = (int)((flim - a + G - 1) / G);
-  const size_t row0 = (size_t)blockIdx.y * wv.rows;
+  const int nfr_total = (int)(flim - a);
+  const int nhop = (int)(b - a);
+  const size_t row0 = (size_t)blockIdx.y * wv.rows + (size_t)(a - wv.wb);
+  const int a_off = (int)(a - wv.wb);
   int cur_chunk = -1;
   int cb = 0;  // carry buffer holding partial sums of the three pending hops
 
   for (int bi = 0; bi < nbatch; ++bi) {
-    const long long fb = a + (long long)bi * G;
+    const int fb = bi * G;                       // frame index relative to a
+    const int nfr = min(G, nfr_total - fb);      // frames present in this batch
 
     // ---- synthesis spectrum Y = smag e^{i theta}, folded for the N/2-point complex inverse
 #pragma unroll 1
-    for (int gg = 0; gg < G; ++gg) {
-      const long long ff = fb + gg;
-      if (ff >= flim) break;
-      const int ca = (int)((ff - wv.wb) / wv.CA);
+    for (int gg = 0; gg < nfr; ++gg) {
+      const int ca = (a_off + fb + gg) / wv.CA;
       if (ca != cur_chunk) {
         cur_chunk = ca;
-        const size_t prow = ((size_t)blockIdx.y * wv.nchunksA + ca) * NBP;
+        const uint32_t* pp = sc.pre + ((size_t)blockIdx.y * wv.nchunksA + ca) * NBP;
 #pragma unroll
         for (int q = 0; q < QP; ++q) {
-          const int k = tid + q * THREADS;
-          if (k > NC / 2) continue;
-          prek[q] = sc.pre[prow + k];
-          prem[q] = sc.pre[prow + NC - k];
+          const int k = 1 + tid + q * THREADS;
+          if (k <= NC / 2) {
+            prek[q] = __ldg(pp + k);
+            prem[q] = __ldg(pp + NC - k);
+          }
+        }
+        if (tid == 0) {
+          pre0 = __ldg(pp);
+          pren = __ldg(pp + NC);
         }
       }
-      const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
+      const float* msrc = sc.smag + (row0 + fb + gg) * NBP;
+      const uint32_t* asrc = sc.lacc + (row0 + fb + gg) * NBP;
       C* zb = buf + gg * BUF;
+      float mk[QP], mm[QP];
+      uint32_t ak[QP], am[QP];
 #pragma unroll
       for (int q = 0; q < QP; ++q) {
-        const int k = tid + q * THREADS;
-        if (k > NC / 2) continue;
-        const int mbin = NC - k;
-        const float mk = sc.smag[row + k], mm = sc.smag[row + mbin];
-        const uint32_t ak = prek[q] + sc.lacc[row + k], am = prem[q] + sc.lacc[row + mbin];
-        float sk, ck, sm, cm;
-        sincospif((float)(int)ak * 4.656612873077393e-10f, &sk, &ck);
-        sincospif((float)(int)am * 4.656612873077393e-10f, &sm, &cm);
-        if (k == 0) {
-          const float y0 = mk * ck, yn = mm * cm;  // Im of DC / Nyquist forced to 0
-          zb[fft_pad(0)] = C{y0 + yn, y0 - yn};
-        } else {
-          const float ykr = mk * ck, yki = mk * sk, ymr = mm * cm, ymi = mm * sm;
+        const int k = 1 + tid + q * THREADS;
+        if (k <= NC / 2) {
+          mk[q] = __ldg(msrc + k);
+          mm[q] = __ldg(msrc + NC - k);
+          ak[q] = __ldg(asrc + k);
+          am[q] = __ldg(asrc + NC - k);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < QP; ++q) {
+        const int k = 1 + tid + q * THREADS;
+        if (k <= NC / 2) {
+          const int mbin = NC - k;
+          float sk, ck, sm, cm;
+          sincos_turns(prek[q] + ak[q], sk, ck);
+          sincos_turns(prem[q] + am[q], sm, cm);
+          const float ykr = mk[q] * ck, yki = mk[q] * sk, ymr = mm[q] * cm, ymi = mm[q] * sm;
           // A = Y_k, B = conj(Y_m): E2 = A + B, D2 = A - B, O2 = D2 * conj(W^k)
           const float er = ykr + ymr, ei = yki - ymi;
           const float dr = ykr - ymr, di = yki + ymi;
@@ -450,25 +594,29 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
           if (mbin != k) zb[fft_pad(mbin)] = C{er + oi, orr - ei};
         }
       }
+      if (tid == 0) {  // Im of DC / Nyquist forced to 0
+        float s0, c0, sn, cn;
+        sincos_turns(pre0 + __ldg(asrc), s0, c0);
+        sincos_turns(pren + __ldg(asrc + NC), sn, cn);
+        const float y0 = __ldg(msrc) * c0, yn = __ldg(msrc + NC) * cn;
+        zb[0] = C{y0 + yn, y0 - yn};
+      }
     }
     __syncthreads();
 
     // ---- inverse FFT, synthesis window (includes gain and 1/N), result in place as real pairs
-    {
-      const long long fg = fb + g;
-      if (fg < flim) {
-        C x[16];
-        C* zb = buf + g * BUF;
-        F::load(x, zb, t);
-        bar.sync();
-        F::run(x, zb, t, twd, bar);
+    if (g < nfr) {
+      C x[16];
+      C* zb = buf + g * BUF;
+      F::load(x, zb, t);
+      bar.sync();
+      F::run(x, zb, t, twd, bar);
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          x[m].x *= wreg[2 * m];
-          x[m].y *= wreg[2 * m + 1];
-        }
-        F::store(x, zb, t);
+      for (int m = 0; m < 16; ++m) {
+        x[m].x *= wreg[2 * m];
+        x[m].y *= wreg[2 * m + 1];
       }
+      F::store(x, zb, t);
     }
     __syncthreads();
 
@@ -476,26 +624,29 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     //      y_f[(h-f+3)H + i], added in ascending f.  This batch completes hops fb-3 .. fb+G-4 and
     //      leaves partial sums of the last three in the other carry buffer.
     {
-      const float* cin = carry + cb * 3 * H;
-      float* cout = carry + (cb ^ 1) * 3 * H;
-      const long long last_f = min(fb + G, flim) - 1;
-      for (int it = tid; it < (G + 3) * (H / 2); it += THREADS) {
-        const int hh = it / (H / 2), i2 = it % (H / 2);
-        const long long h = fb - 3 + hh;
-        if (h < a) continue;  // hops before the chunk belong to the previous CTA
+      const float2* cin = carry + cb * 3 * H2;
+      float2* cout = carry + (cb ^ 1) * 3 * H2;
+      const int h_min = (bi == 0) ? 0 : -3;  // hops before the chunk belong to the previous CTA
+      const int last_g = nfr - 1;
+      const int last_needed_cap = nfr_total - 1 - fb;  // index (relative to fb) of the chunk's last frame
+#pragma unroll 1
+      for (int it = tid; it < (G + 3) * H2; it += THREADS) {
+        const int hh = it / H2, i2 = it % H2;
+        const int hr = hh - 3;  // hop relative to fb
+        if (hr < h_min) continue;
         float2 s = make_float2(0.f, 0.f);
-        if (hh < 3) s = *reinterpret_cast<const float2*>(cin + hh * H + 2 * i2);
-        const long long f_lo = max(h, fb), f_hi = min(h + 3, last_f);
-        for (long long f = f_lo; f <= f_hi; ++f) {
-          const int cidx = (int)(h - f + 3) * (H / 2) + i2;  // complex index inside frame f
-          const C v = buf[(int)(f - fb) * BUF + fft_pad(cidx)];
+        if (hh < 3) s = cin[hh * H2 + i2];
+        const int g_lo = max(hr, 0), g_hi = min(hr + 3, last_g);
+        for (int gi = g_lo; gi <= g_hi; ++gi) {
+          const C v = buf[gi * BUF + fft_pad((hr - gi + 3) * H2 + i2)];
           s.x += v.x;
           s.y += v.y;
         }
-        const bool complete = min(h + 3, flim - 1) <= last_f;
+        const bool complete = min(hr + 3, last_needed_cap) <= last_g;
         if (complete) {
-          if (h < b) {
-            const long long o = h * H + 2 * i2;
+          const int hrel = fb + hr;  // hop relative to a
+          if (hrel < nhop) {
+            const long long o = (a + hrel) * H + 2 * i2;
             if (o + 1 < tr.n) {
               *reinterpret_cast<float2*>(tr.out + o) = s;
             } else if (o < tr.n) {
@@ -503,7 +654,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
             }
           }
         } else {
-          *reinterpret_cast<float2*>(cout + (hh - G) * H + 2 * i2) = s;
+          cout[(hh - G) * H2 + i2] = s;
         }
       }
       cb ^= 1;

@@ -65,6 +65,18 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._L.mlx_launch_count(self._h))
 
+    KERNEL_KINDS = ("pv_analyze", "pv_scan", "pv_synth", "spec", "grain")
+
+    def profile_enable(self, on: bool = True) -> None:
+        check(self._L.mlx_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{kernel: (total_ms, launches)} measured with CUDA events on the engine stream."""
+        ms = (C.c_double * 5)()
+        ln = (C.c_int64 * 5)()
+        check(self._L.mlx_profile_read(self._h, ms, ln, int(reset)))
+        return {k: (ms[i], int(ln[i])) for i, k in enumerate(self.KERNEL_KINDS)}
+
     # ------------------------------------------------------------------ tracks
     def upload_tracks(self, tracks: Sequence[np.ndarray]) -> None:
         arrs = [np.ascontiguousarray(t, np.float32) for t in tracks]

@@ -46,6 +46,20 @@ def main():
             print(f"pv N={N:5d} st={semis:+.0f} rms={rms(g['y'], o['y']):.3e} max={np.abs(g['y'] - o['y']).max():.3e} "
                   f"peak_eq={np.array_equal(g['peak'][ok], o['peak'][ok])} ({(~ok).sum()} excl) "
                   f"f0_max={np.abs(g['f0'] - o['f0']).max():.3e} gpu_s={t1 - t0:.4f}")
+    # drift: long stationary tones (systematic per-frame phase errors would grow linearly in time)
+    n = 300 * 48000
+    t = np.arange(n) / 48000.0
+    xs = (0.3 * np.sin(2 * np.pi * 441.3 * t) + 0.15 * np.sin(2 * np.pi * 1237.7 * t + 0.3)
+          + 1e-4 * np.random.default_rng(5).standard_normal(n)).astype(np.float32)
+    eng.upload_tracks([xs])
+    r = m.semitone_ratio(3.0)
+    g = eng.pv_run(2048, 512, r)[0]
+    o = O.pv_run(xs, 2048, 512, r)
+    seg = 5 * 48000
+    print(f"drift 300 s stationary: rms first 5 s {rms(g['y'][:seg], o['y'][:seg]):.3e}  "
+          f"mid {rms(g['y'][n // 2:n // 2 + seg], o['y'][n // 2:n // 2 + seg]):.3e}  "
+          f"last 5 s {rms(g['y'][-seg:], o['y'][-seg:]):.3e}  whole {rms(g['y'], o['y']):.3e} "
+          f"peak_eq={np.array_equal(g['peak'], o['peak'])}")
     # multi-track ragged + wave tiling
     xs = [S.vibrato_tone(2.0, seed=1), S.vibrato_tone(1.37, seed=2, f_base=330.0), S.vibrato_tone(0.2, seed=3)]
     eng.upload_tracks(xs)
