@@ -393,10 +393,10 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
       const int* dl = s_del + gg * NBP;
       const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
       float r = wv.rate;
-      unsigned long long r_fix = (unsigned long long)wv.r_fix;
+      uint32_t r_fix = (uint32_t)wv.r_fix;  // rate * 2^26 <= 2^28
       if (per_frame_rate) {
         r = tr.rate_pf[ff];
-        r_fix = (unsigned long long)((double)r * 67108864.0);
+        r_fix = (uint32_t)((double)r * 67108864.0);
       }
       const bool counted = ff < wv.we;
 #pragma unroll
@@ -410,18 +410,22 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
             kk = __ldg(wv.gk + j);
           }
           const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
-          float smag = 0.f;
-          uint32_t inc = ((uint32_t)j & 3u) << 30;  // empty K_j: s_nu = j -> frac(j / 4)
-          if (klo <= khi) {
-            for (int k = klo; k <= khi; ++k) smag += fabsf(mg[k]);
-            // frac(rate * nu / 4) * 2^32 with nu/4 = (khi * 2^30 + d) / 2^32 turns, d the signed
-            // phase advance (+-2^32 when the cut decision says so): one exact 64-bit product mod 2^64,
-            // rounded once -- the same single rounding per frame as the oracle's llrint.
-            long long dd = (long long)dl[khi];
-            if (__float_as_uint(mg[khi]) >> 31) dd += (dd < 0) ? 4294967296LL : -4294967296LL;
-            const unsigned long long nu = (unsigned long long)(((long long)khi << 30) + dd);
-            inc = (uint32_t)((r_fix * nu + (1ULL << 25)) >> 26);
-          }
+          const bool any = klo <= khi;       // K_j non-empty (at most one bin when rate >= 1)
+          const int kh = any ? khi : 0;
+          float smag = any ? fabsf(mg[klo]) : 0.f;
+          for (int k = klo + 1; k <= khi; ++k) smag += fabsf(mg[k]);  // only when rate < 1
+          // frac(rate * nu / 4) * 2^32 with nu / 4 = (khi * 2^30 + d) / 2^32 turns, d the signed phase
+          // advance (+-2^32 when the cut decision says so): one exact product mod 2^64, rounded once
+          // -- the same single rounding per frame as the oracle's llrint.  32-bit pieces:
+          const int d32 = dl[kh];
+          int dhi = d32 >> 31;
+          dhi += (__float_as_uint(mg[kh]) >> 31) ? ((d32 < 0) ? 1 : -1) : 0;
+          const uint32_t k30 = (uint32_t)kh << 30;
+          const uint32_t nlo = k30 + (uint32_t)d32;
+          const uint32_t nhi = (uint32_t)(kh >> 2) + (uint32_t)dhi + (nlo < k30 ? 1u : 0u);
+          const unsigned long long prod =
+              (unsigned long long)r_fix * nlo + ((unsigned long long)(r_fix * nhi) << 32) + (1ULL << 25);
+          const uint32_t inc = any ? (uint32_t)(prod >> 26) : (((uint32_t)j & 3u) << 30);
           lacc[q] += inc;
           if (counted) tot[q] = lacc[q];
           sc.smag[row + j] = smag;
@@ -493,6 +497,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NBP = Cfg::NBP;
   constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUF, QP = Cfg::QP;
   constexpr int H2 = H / 2;
+  constexpr int GS = G < 4 ? G : 4;  // frames whose loads are in flight together
   using C = cplx<float>;
   using F = Fft<float, NC, +1>;
 
@@ -535,71 +540,88 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   const int nhop = (int)(b - a);
   const size_t row0 = (size_t)blockIdx.y * wv.rows + (size_t)(a - wv.wb);
   const int a_off = (int)(a - wv.wb);
-  int cur_chunk = -1;
-  int cb = 0;  // carry buffer holding partial sums of the three pending hops
+  int next_chunk_at = 0;  // frame (relative to a) at which the analysis chunk, hence the prefix, changes
+  int cb = 0;             // carry buffer holding partial sums of the three pending hops
 
   for (int bi = 0; bi < nbatch; ++bi) {
     const int fb = bi * G;                       // frame index relative to a
     const int nfr = min(G, nfr_total - fb);      // frames present in this batch
 
-    // ---- synthesis spectrum Y = smag e^{i theta}, folded for the N/2-point complex inverse
+    // ---- synthesis spectrum Y = smag e^{i theta}, folded for the N/2-point complex inverse.
+    //      All global loads of a sub-batch are issued before the first use (latency hiding).
 #pragma unroll 1
-    for (int gg = 0; gg < nfr; ++gg) {
-      const int ca = (a_off + fb + gg) / wv.CA;
-      if (ca != cur_chunk) {
-        cur_chunk = ca;
-        const uint32_t* pp = sc.pre + ((size_t)blockIdx.y * wv.nchunksA + ca) * NBP;
+    for (int g0 = 0; g0 < nfr; g0 += GS) {
+      float mk[GS][QP], mm[GS][QP], m0[GS], mn[GS];
+      uint32_t ak[GS][QP], am[GS][QP], a0[GS], an[GS];
+#pragma unroll
+      for (int u = 0; u < GS; ++u) {
+        const int gg = min(g0 + u, nfr - 1);  // clamp: duplicates of the last frame are never used
+        const float* msrc = sc.smag + (row0 + fb + gg) * NBP;
+        const uint32_t* asrc = sc.lacc + (row0 + fb + gg) * NBP;
 #pragma unroll
         for (int q = 0; q < QP; ++q) {
           const int k = 1 + tid + q * THREADS;
           if (k <= NC / 2) {
-            prek[q] = __ldg(pp + k);
-            prem[q] = __ldg(pp + NC - k);
+            mk[u][q] = __ldg(msrc + k);
+            mm[u][q] = __ldg(msrc + NC - k);
+            ak[u][q] = __ldg(asrc + k);
+            am[u][q] = __ldg(asrc + NC - k);
           }
         }
         if (tid == 0) {
-          pre0 = __ldg(pp);
-          pren = __ldg(pp + NC);
-        }
-      }
-      const float* msrc = sc.smag + (row0 + fb + gg) * NBP;
-      const uint32_t* asrc = sc.lacc + (row0 + fb + gg) * NBP;
-      C* zb = buf + gg * BUF;
-      float mk[QP], mm[QP];
-      uint32_t ak[QP], am[QP];
-#pragma unroll
-      for (int q = 0; q < QP; ++q) {
-        const int k = 1 + tid + q * THREADS;
-        if (k <= NC / 2) {
-          mk[q] = __ldg(msrc + k);
-          mm[q] = __ldg(msrc + NC - k);
-          ak[q] = __ldg(asrc + k);
-          am[q] = __ldg(asrc + NC - k);
+          m0[u] = __ldg(msrc);
+          mn[u] = __ldg(msrc + NC);
+          a0[u] = __ldg(asrc);
+          an[u] = __ldg(asrc + NC);
         }
       }
 #pragma unroll
-      for (int q = 0; q < QP; ++q) {
-        const int k = 1 + tid + q * THREADS;
-        if (k <= NC / 2) {
-          const int mbin = NC - k;
-          float sk, ck, sm, cm;
-          sincos_turns(prek[q] + ak[q], sk, ck);
-          sincos_turns(prem[q] + am[q], sm, cm);
-          const float ykr = mk[q] * ck, yki = mk[q] * sk, ymr = mm[q] * cm, ymi = mm[q] * sm;
-          // A = Y_k, B = conj(Y_m): E2 = A + B, D2 = A - B, O2 = D2 * conj(W^k)
-          const float er = ykr + ymr, ei = yki - ymi;
-          const float dr = ykr - ymr, di = yki + ymi;
-          const float orr = dr * wr[q].x + di * wr[q].y, oi = di * wr[q].x - dr * wr[q].y;
-          zb[fft_pad(k)] = C{er - oi, ei + orr};
-          if (mbin != k) zb[fft_pad(mbin)] = C{er + oi, orr - ei};
+      for (int u = 0; u < GS; ++u) {
+        const int gg = g0 + u;
+        if (gg < nfr) {
+          if (fb + gg >= next_chunk_at) {  // entered the next analysis chunk: reload its phase prefix
+            const int ca = (a_off + fb + gg) / wv.CA;
+            next_chunk_at = (ca + 1) * wv.CA - a_off;
+            const uint32_t* pp = sc.pre + ((size_t)blockIdx.y * wv.nchunksA + ca) * NBP;
+#pragma unroll
+            for (int q = 0; q < QP; ++q) {
+              const int k = 1 + tid + q * THREADS;
+              if (k <= NC / 2) {
+                prek[q] = __ldg(pp + k);
+                prem[q] = __ldg(pp + NC - k);
+              }
+            }
+            if (tid == 0) {
+              pre0 = __ldg(pp);
+              pren = __ldg(pp + NC);
+            }
+          }
+          C* zb = buf + gg * BUF;
+#pragma unroll
+          for (int q = 0; q < QP; ++q) {
+            const int k = 1 + tid + q * THREADS;
+            if (k <= NC / 2) {
+              const int mbin = NC - k;
+              float sk, ck, sm, cm;
+              sincos_turns(prek[q] + ak[u][q], sk, ck);
+              sincos_turns(prem[q] + am[u][q], sm, cm);
+              const float ykr = mk[u][q] * ck, yki = mk[u][q] * sk, ymr = mm[u][q] * cm, ymi = mm[u][q] * sm;
+              // A = Y_k, B = conj(Y_m): E2 = A + B, D2 = A - B, O2 = D2 * conj(W^k)
+              const float er = ykr + ymr, ei = yki - ymi;
+              const float dr = ykr - ymr, di = yki + ymi;
+              const float orr = dr * wr[q].x + di * wr[q].y, oi = di * wr[q].x - dr * wr[q].y;
+              zb[fft_pad(k)] = C{er - oi, ei + orr};
+              if (mbin != k) zb[fft_pad(mbin)] = C{er + oi, orr - ei};
+            }
+          }
+          if (tid == 0) {  // Im of DC / Nyquist forced to 0
+            float s0, c0, sn, cn;
+            sincos_turns(pre0 + a0[u], s0, c0);
+            sincos_turns(pren + an[u], sn, cn);
+            const float y0 = m0[u] * c0, yn = mn[u] * cn;
+            zb[0] = C{y0 + yn, y0 - yn};
+          }
         }
-      }
-      if (tid == 0) {  // Im of DC / Nyquist forced to 0
-        float s0, c0, sn, cn;
-        sincos_turns(pre0 + __ldg(asrc), s0, c0);
-        sincos_turns(pren + __ldg(asrc + NC), sn, cn);
-        const float y0 = __ldg(msrc) * c0, yn = __ldg(msrc + NC) * cn;
-        zb[0] = C{y0 + yn, y0 - yn};
       }
     }
     __syncthreads();
