@@ -95,7 +95,7 @@ struct mlx_ctx {
   std::map<int, Tables> tables;
 
   // phase-vocoder scratch
-  DevBuf smag, lacc, tot, pre, carry, track_desc, ptr_stage, gk;
+  DevBuf smag, lacc, tot, totc, pre, carry, track_desc, ptr_stage, gk;
   DevBuf out_wav, out_peak, out_f0;  // device results for the host-pointer entry points
   DevBuf jobs, spec_out, spec_rgb;
   DevBuf g_i32a, g_i32b, g_f32a, g_f32b, g_i64, g_out, g_out16;
@@ -265,6 +265,7 @@ int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth,
   CK(c->smag.reserve(sizeof(float) * nt * rows * pl.NBP));
   CK(c->lacc.reserve(sizeof(uint32_t) * nt * rows * pl.NBP));
   CK(c->tot.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
+  CK(c->totc.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
   CK(c->pre.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
   CK(c->carry.reserve(sizeof(uint32_t) * nt * pl.NBP));
   CK(c->track_desc.reserve(sizeof(PvTrack) * nt));
@@ -299,7 +300,7 @@ int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth,
               static_cast<const float*>(tb->win.p),         static_cast<const double*>(tb->win_d.p),
               static_cast<const float*>(tb->wsyn.p)};
   PvScratch sc{static_cast<float*>(c->smag.p), static_cast<uint32_t*>(c->lacc.p), static_cast<uint32_t*>(c->tot.p),
-               static_cast<uint32_t*>(c->pre.p), static_cast<uint32_t*>(c->carry.p)};
+               static_cast<uint32_t*>(c->totc.p), static_cast<uint32_t*>(c->pre.p), static_cast<uint32_t*>(c->carry.p)};
   const PvTrack* tdev = static_cast<const PvTrack*>(c->track_desc.p);
 
   // bin-shift table for the constant rate (PV-spec A.5): one float multiply per bin, as the spec says
@@ -405,7 +406,7 @@ void mlx_destroy(mlx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&c->gk, &c->track_buf, &c->smag, &c->lacc, &c->tot, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
+  for (DevBuf* b : {&c->gk, &c->track_buf, &c->smag, &c->lacc, &c->tot, &c->totc, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
                     &c->out_wav, &c->out_peak, &c->out_f0, &c->jobs, &c->spec_out, &c->spec_rgb, &c->g_i32a,
                     &c->g_i32b, &c->g_f32a, &c->g_f32b, &c->g_i64, &c->g_out, &c->g_out16})
     b->release();

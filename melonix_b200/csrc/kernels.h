@@ -53,7 +53,8 @@ struct PvWave {
 struct PvScratch {
   float* smag;      // [ntracks][rows][NBP]  shifted magnitudes
   uint32_t* lacc;   // [ntracks][rows][NBP]  chunk-local inclusive phase sums
-  uint32_t* tot;    // [ntracks][nchunksA][NBP] chunk totals over frames < we
+  uint32_t* tot;    // [ntracks][nchunksA][NBP] chunk totals over all frames of the chunk
+  uint32_t* totc;   // [ntracks][nchunksA][NBP] chunk totals over its frames < we (carry to the next wave)
   uint32_t* pre;    // [ntracks][nchunksA][NBP] exclusive prefix (incl. carry)
   uint32_t* carry;  // [ntracks][NBP] running phase at frame wb (updated to `we` by the scan)
 };

@@ -246,7 +246,10 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   const long long a = wv.wb + (long long)blockIdx.x * wv.CA;
   const size_t trow = ((size_t)blockIdx.y * wv.nchunksA + blockIdx.x) * NBP;
   if (a >= lim) {  // chunk past the end of this track: contributes nothing to the scan
-    for (int j = tid; j < NB; j += THREADS) sc.tot[trow + j] = 0u;
+    for (int j = tid; j < NB; j += THREADS) {
+      sc.tot[trow + j] = 0u;
+      sc.totc[trow + j] = 0u;
+    }
     return;
   }
   const long long b = min(a + (long long)wv.CA, lim);
@@ -282,9 +285,9 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   double p0 = 1.0, pn = 1.0;  // previous X[0], X[NC] (real)
   uint32_t pp0 = 0u, ppn = 0u;
   float pm0 = 1.f, pmn = 1.f;
-  uint32_t lacc[QB], tot[QB];
+  uint32_t lacc[QB], totc[QB];  // chunk-local phase sum; its value at the last frame < we
 #pragma unroll
-  for (int q = 0; q < QB; ++q) lacc[q] = tot[q] = 0u;
+  for (int q = 0; q < QB; ++q) lacc[q] = totc[q] = 0u;
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
   const size_t row0 = (size_t)blockIdx.y * wv.rows;
   const bool per_frame_rate = tr.rate_pf != nullptr;
@@ -427,7 +430,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
               (unsigned long long)r_fix * nlo + ((unsigned long long)(r_fix * nhi) << 32) + (1ULL << 25);
           const uint32_t inc = any ? (uint32_t)(prod >> 26) : (((uint32_t)j & 3u) << 30);
           lacc[q] += inc;
-          if (counted) tot[q] = lacc[q];
+          if (counted) totc[q] = lacc[q];
           sc.smag[row + j] = smag;
           sc.lacc[row + j] = lacc[q];
         }
@@ -469,7 +472,10 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 #pragma unroll
   for (int q = 0; q < QB; ++q) {
     const int j = tid + q * THREADS;
-    if (j < NB) sc.tot[trow + j] = tot[q];
+    if (j < NB) {
+      sc.tot[trow + j] = lacc[q];    // all frames of the chunk: prefix of the later chunks of this wave
+      sc.totc[trow + j] = totc[q];   // frames < we only: what the next wave starts from
+    }
   }
 }
 
@@ -479,13 +485,15 @@ __global__ void pv_scan_kernel(int nb, int nbp, int nchunks, const PvScratch sc)
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nb) return;
   const size_t tr = blockIdx.y;
-  uint32_t run = sc.carry[tr * nbp + j];
+  const uint32_t carry = sc.carry[tr * nbp + j];
+  uint32_t run = carry, counted = carry;
   for (int c = 0; c < nchunks; ++c) {
     const size_t i = (tr * nchunks + c) * nbp + j;
     sc.pre[i] = run;
     run += sc.tot[i];
+    counted += sc.totc[i];
   }
-  sc.carry[tr * nbp + j] = run;
+  sc.carry[tr * nbp + j] = counted;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -648,7 +656,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     {
       const float2* cin = carry + cb * 3 * H2;
       float2* cout = carry + (cb ^ 1) * 3 * H2;
-      const int h_min = (bi == 0) ? 0 : -3;  // hops before the chunk belong to the previous CTA
+      const int h_min = -min(3, fb);  // hops before the chunk's first (fb + hr < 0) belong to the previous CTA
       const int last_g = nfr - 1;
       const int last_needed_cap = nfr_total - 1 - fb;  // index (relative to fb) of the chunk's last frame
 #pragma unroll 1

@@ -1,0 +1,167 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on B200s, gloo in the CPU tests).
+
+Two sharding modes:
+
+* independent tracks (BASELINE configs[2]): `shard_tracks` -- contiguous blocks of tracks per rank,
+  no data-path collective at all.
+* one long file sharded by contiguous time range (configs[3]): rank r owns frames
+  [F*r/G, F*(r+1)/G).  Two small exchanges per track:
+    1. seam samples: the analysis of a rank's first frame needs the `fftN` samples before its range
+       (and one hop more for the halo frame), its last three overlap-add hops need `3*hop` samples
+       after it -> one batched NCCL send/recv with each neighbour (`exchange_seam_samples`);
+    2. phase carry: the exact uint32 per-bin phase totals of every rank's owned frames
+       (fftN/2+1 values) are all-gathered and prefix-summed (`exclusive_phase_prefix`); integer
+       addition is associative, so the sharded result is bit-identical to the unsharded one.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+def shard_tracks(ntracks: int, world: int, rank: int) -> range:
+    """Contiguous block of track indices owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(ntracks, world)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+def num_frames(n: int, hop: int) -> int:
+    return (n + hop - 1) // hop
+
+
+@dataclass(frozen=True)
+class TimeShard:
+    """Frame range owned by one rank and the sample window it must hold (global indices)."""
+    rank: int
+    frame_begin: int       # first owned frame (global)
+    frame_end: int         # one past the last owned frame (global)
+    own_lo: int            # owned samples [own_lo, own_hi) = output hops of the owned frames
+    own_hi: int
+    need_lo: int           # samples the rank must hold: [need_lo, need_hi), includes both halos
+    need_hi: int
+    frame_offset: int      # local frame index = global frame index - frame_offset
+
+    @property
+    def local_frame_begin(self) -> int:
+        return self.frame_begin - self.frame_offset
+
+    @property
+    def local_frame_end(self) -> int:
+        return self.frame_end - self.frame_offset
+
+    @property
+    def left_halo(self) -> int:
+        return self.own_lo - self.need_lo
+
+    @property
+    def right_halo(self) -> int:
+        return self.need_hi - self.own_hi
+
+
+def shard_frames(n: int, fft_n: int, hop: int, world: int, rank: int) -> TimeShard:
+    """Contiguous time-range shard of a track of n samples for `rank` of `world`."""
+    F = num_frames(n, hop)
+    fb = F * rank // world
+    fe = F * (rank + 1) // world
+    # frame f covers samples [(f-3)*hop, (f+1)*hop) (fft_n = 4*hop).  Needed frames: fb-1 (halo whose
+    # spectrum seeds the phase difference) .. fe+2 (their tails overlap-add into the owned hops).
+    off = max(fb - 4, 0)
+    need_lo = off * hop
+    need_hi = min(n, (fe + 3) * hop)
+    own_lo = min(n, fb * hop)
+    own_hi = min(n, fe * hop)
+    return TimeShard(rank, fb, fe, own_lo, own_hi, need_lo, need_hi, off)
+
+
+def exchange_seam_samples(own: torch.Tensor, shard: TimeShard, world: int, group=None) -> torch.Tensor:
+    """Builds the rank's sample window [need_lo, need_hi) from its owned samples plus the seam samples
+    of its two neighbours: ONE batched send/recv (left neighbour's tail, right neighbour's head).
+    `own` holds samples [own_lo, own_hi) on the compute device.  Every rank must call this."""
+    rank = shard.rank
+    left, right = shard.left_halo, shard.right_halo
+    buf = torch.zeros(left + own.numel() + right, dtype=own.dtype, device=own.device)
+    buf[left:left + own.numel()] = own
+    ops = []
+    if rank > 0 and left > 0:
+        ops.append(dist.P2POp(dist.irecv, buf[:left], rank - 1, group))
+    if rank + 1 < world and right > 0:
+        ops.append(dist.P2POp(dist.irecv, buf[left + own.numel():], rank + 1, group))
+    # what the neighbours need from this rank is determined by THEIR shard; all ranks use the same rule
+    send_bufs = []
+    if rank + 1 < world:
+        nxt = _neighbour_need(shard, +1)
+        if nxt > 0:
+            send_bufs.append(own[own.numel() - nxt:].contiguous())
+            ops.append(dist.P2POp(dist.isend, send_bufs[-1], rank + 1, group))
+    if rank > 0:
+        prv = _neighbour_need(shard, -1)
+        if prv > 0:
+            send_bufs.append(own[:prv].contiguous())
+            ops.append(dist.P2POp(dist.isend, send_bufs[-1], rank - 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return buf
+
+
+def _neighbour_need(shard: TimeShard, direction: int) -> int:
+    """Samples of this rank's owned range the neighbour needs (carried in shard by the caller via
+    `with_neighbours`).  Stored as attributes to keep TimeShard a plain value type."""
+    return getattr(shard, "_to_right" if direction > 0 else "_to_left")
+
+
+def plan_time_shards(n: int, fft_n: int, hop: int, world: int) -> list[TimeShard]:
+    """All ranks' shards, each annotated with how many of its samples its neighbours need."""
+    shards = [shard_frames(n, fft_n, hop, world, r) for r in range(world)]
+    for r, s in enumerate(shards):
+        to_right = shards[r + 1].left_halo if r + 1 < world else 0
+        to_left = shards[r - 1].right_halo if r > 0 else 0
+        if to_right > s.own_hi - s.own_lo or to_left > s.own_hi - s.own_lo:
+            raise ValueError("time shards are shorter than the seam overlap: use fewer ranks for this file")
+        object.__setattr__(s, "_to_right", to_right)
+        object.__setattr__(s, "_to_left", to_left)
+    return shards
+
+
+def exclusive_phase_prefix(totals: torch.Tensor, world: int, rank: int, group=None) -> torch.Tensor:
+    """totals: [ntracks, nbins] int64 holding uint32 values (this rank's phase totals).  Returns the
+    sum over lower ranks modulo 2^32 (the phase carried into this rank's first frame)."""
+    gathered = [torch.empty_like(totals) for _ in range(world)]
+    dist.all_gather(gathered, totals.contiguous(), group=group)
+    acc = torch.zeros_like(totals)
+    for r in range(rank):
+        acc = (acc + gathered[r]) & 0xFFFFFFFF
+    return acc
+
+
+def run_time_sharded(engine, own: torch.Tensor, n_total: int, fft_n: int, hop: int, rate: float,
+                     sample_rate: float = 48000.0, group=None):
+    """Phase-vocodes ONE long mono track sharded by time range across the ranks of `group`.
+
+    own: this rank's owned samples (CUDA float32, global samples [own_lo, own_hi) of
+    plan_time_shards(...)[rank]).  Returns (y_own, peak_own, f0_own): the owned output samples and the
+    owned frames' peak bins / f0, all on the device.  Bit-identical to the unsharded run."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    shard = plan_time_shards(n_total, fft_n, hop, world)[rank]
+    window = exchange_seam_samples(own, shard, world, group)          # seam exchange (1)
+    engine.use_torch_stream()
+    engine.upload_tracks_dev([window])
+    nb = fft_n // 2 + 1
+    lb, le = shard.local_frame_begin, shard.local_frame_end
+    totals32 = torch.zeros(nb, dtype=torch.int32, device=own.device)
+    F_local = num_frames(window.numel(), hop)
+    peak = torch.zeros(F_local, dtype=torch.int32, device=own.device)
+    f0 = torch.zeros(F_local, dtype=torch.float32, device=own.device)
+    engine.pv_phase_totals_dev(fft_n, hop, rate, [totals32], sample_rate=sample_rate, frame_begin=lb,
+                               frame_end=le, wave_mib=-1)
+    totals = (totals32.to(torch.int64) & 0xFFFFFFFF).unsqueeze(0)
+    carry = exclusive_phase_prefix(totals, world, rank, group)[0]   # phase carry (2)
+    carry32 = torch.where(carry >= 2 ** 31, carry - 2 ** 32, carry).to(torch.int32)
+    y = torch.zeros_like(window)
+    engine.pv_run_dev(fft_n, hop, rate, [y], [peak], [f0], sample_rate=sample_rate, frame_begin=lb,
+                      frame_end=le, phase_in=[carry32], wave_mib=-1)
+    lo = shard.left_halo
+    return y[lo:lo + own.numel()], peak[lb:le], f0[lb:le]

@@ -1,0 +1,160 @@
+// melonix_b200/host/host_test.cpp -- headless driver for the C++ drop-in classes (built with
+// -DMELONIX_HEADLESS; runs on the GPU box).  tests/test_host_cpp_gpu.py feeds it raw files and
+// compares what it writes with the oracle.
+//   host_test spec      wav.f32 jobs.i32 out.f32        Spec::getSpec for every job (async contract checked)
+//   host_test speccache wav.f32 k width rangeTime out.u8   SpecCache::getTex for every column
+//   host_test export    wav.f32 sampleRate semitones out.i16   segment -> schedule -> mlx_grain_render
+#include "grain_schedule.hpp"
+#include "spec-cache.hpp"
+#include "spec.hpp"
+
+#include "../../include/melonix_gpu.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <thread>
+
+template <typename T>
+static auto readAll(const char *path) -> std::vector<T>
+{
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f)
+  {
+    std::fprintf(stderr, "cannot open %s\n", path);
+    std::exit(2);
+  }
+  const auto bytes = static_cast<size_t>(f.tellg());
+  std::vector<T> v(bytes / sizeof(T));
+  f.seekg(0);
+  f.read(reinterpret_cast<char *>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
+  return v;
+}
+
+template <typename T>
+static void writeAll(const char *path, const T *p, size_t n)
+{
+  std::ofstream f(path, std::ios::binary);
+  f.write(reinterpret_cast<const char *>(p), static_cast<std::streamsize>(n * sizeof(T)));
+}
+
+static int runSpec(char **a)
+{
+  auto wav = readAll<float>(a[0]);
+  const auto jobs = readAll<int32_t>(a[1]);
+  const int count = static_cast<int>(jobs.size() / 2);
+  const int half = Spec::spectrSize() / 2;
+  Spec spec(std::span<float>{wav.data(), wav.size()});
+  // KAT-3: the first call of a key is a miss and must return {} without blocking
+  int firstEmpty = 0;
+  for (int j = 0; j < count; ++j)
+    firstEmpty += spec.getSpec(jobs[2 * j], jobs[2 * j + 1]).empty();
+  std::vector<float> out(static_cast<size_t>(count) * half, -1.f);
+  std::vector<char> done(count, 0);
+  int remaining = count;
+  for (int spin = 0; remaining > 0 && spin < 20000; ++spin)
+  {
+    for (int j = 0; j < count; ++j)
+    {
+      if (done[j])
+        continue;
+      const auto s = spec.getSpec(jobs[2 * j], jobs[2 * j + 1]);
+      if (s.empty())
+        continue;
+      if (static_cast<int>(s.size()) != half)
+      {
+        std::fprintf(stderr, "bad length %zu\n", s.size());
+        return 3;
+      }
+      std::memcpy(out.data() + static_cast<size_t>(j) * half, s.data(), sizeof(float) * half);
+      done[j] = 1;
+      --remaining;
+    }
+    if (remaining)
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
+  writeAll(a[2], out.data(), out.size());
+  std::printf("spec: jobs=%d first_call_empty=%d remaining=%d half=%d\n", count, firstEmpty, remaining, half);
+  return remaining == 0 ? 0 : 4;
+}
+
+static int runSpecCache(char **a)
+{
+  auto wav = readAll<float>(a[0]);
+  const float k = static_cast<float>(std::atof(a[1]));
+  const int width = std::atoi(a[2]);
+  const double rangeTime = std::atof(a[3]);
+  const int sampleRate = 48000;
+  const int half = Spec::spectrSize() / 2;
+  Spec spec(std::span<float>{wav.data(), wav.size()});
+  SpecCache cache(spec, k, width, rangeTime, [&](double t) { return static_cast<int>(t * sampleRate); });
+  std::vector<GLuint> names(width);
+  auto &gl = gl_headless::state();
+  int black = width;
+  for (int spin = 0; black > 0 && spin < 20000; ++spin)
+  {
+    black = 0;
+    for (int x = 0; x < width; ++x)
+    {
+      names[x] = cache.getTex(x * rangeTime / width + 1e-9);
+      black += gl.tex[names[x]].size() != static_cast<size_t>(half) * 3;
+    }
+    if (black)
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
+  std::vector<unsigned char> out(static_cast<size_t>(width) * half * 3);
+  for (int x = 0; x < width && black == 0; ++x)
+    std::memcpy(out.data() + static_cast<size_t>(x) * half * 3, gl.tex[names[x]].data(), static_cast<size_t>(half) * 3);
+  writeAll(a[4], out.data(), out.size());
+  std::printf("speccache: columns=%d not_ready=%d half=%d\n", width, black, half);
+  cache.clear();
+  return black == 0 ? 0 : 4;
+}
+
+static int runExport(char **a)
+{
+  auto wav = readAll<float>(a[0]);
+  const int sampleRate = std::atoi(a[1]);
+  const double semis = std::atof(a[2]);
+  const auto grains = melonix::segmentGrains(wav);
+  // a constant shift needs a marker near each end
+  std::vector<melonix::MarkerView> markers;
+  if (semis != 0.0)
+    markers = {{10, 0.0, semis}, {static_cast<int>(wav.size()) - 10, 0.0, semis}};
+  const auto s = melonix::buildExportSchedule(wav, sampleRate, markers, grains);
+  mlx_ctx *ctx = nullptr;
+  if (mlx_create(&ctx, 0) != MLX_OK)
+  {
+    std::fprintf(stderr, "%s\n", mlx_last_error());
+    return 5;
+  }
+  const float *ptr = wav.data();
+  const int64_t n = static_cast<int64_t>(wav.size());
+  int rc = mlx_upload_tracks(ctx, &ptr, &n, 1);
+  const int rows = static_cast<int>(s.gStart.size());
+  std::vector<int16_t> pcm16(static_cast<size_t>(s.outOff.back() + s.tailZeros));
+  if (rc == MLX_OK)
+    rc = mlx_grain_render(ctx, 0, s.gStart.data(), s.gLen.data(), s.rate.data(), s.outOff.data(), s.next.data(), rows,
+                          s.tailZeros, nullptr, pcm16.data());
+  if (rc != MLX_OK)
+    std::fprintf(stderr, "%s\n", mlx_last_error());
+  mlx_destroy(ctx);
+  writeAll(a[3], pcm16.data(), pcm16.size());
+  std::printf("export: grains=%zu rows=%d samples=%zu\n", grains.size(), rows, pcm16.size());
+  return rc == MLX_OK ? 0 : 6;
+}
+
+int main(int argc, char **argv)
+{
+  if (argc >= 5 && !std::strcmp(argv[1], "spec"))
+    return runSpec(argv + 2);
+  if (argc >= 7 && !std::strcmp(argv[1], "speccache"))
+    return runSpecCache(argv + 2);
+  if (argc >= 6 && !std::strcmp(argv[1], "export"))
+    return runExport(argv + 2);
+  std::fprintf(stderr, "usage: host_test spec|speccache|export ...\n");
+  return 1;
+}

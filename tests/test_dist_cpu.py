@@ -1,0 +1,69 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in melonix_b200/dist.py."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from melonix_b200 import dist as D  # noqa: E402
+
+
+def test_shard_tracks_partition():
+    for n in (1, 7, 64, 65):
+        for w in (1, 2, 3, 8):
+            got = [i for r in range(w) for i in D.shard_tracks(n, w, r)]
+            assert got == list(range(n))
+            sizes = [len(D.shard_tracks(n, w, r)) for r in range(w)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_time_shards_cover_and_halo():
+    n, N, H = 48000 * 20 + 123, 4096, 1024
+    for w in (1, 2, 4, 8):
+        sh = D.plan_time_shards(n, N, H, w)
+        assert sh[0].frame_begin == 0 and sh[-1].frame_end == D.num_frames(n, H)
+        for a, b in zip(sh[:-1], sh[1:]):
+            assert a.frame_end == b.frame_begin and a.own_hi == b.own_lo
+        for s in sh:
+            assert s.need_lo <= s.own_lo <= s.own_hi <= s.need_hi <= n
+            assert s.need_lo == max(0, (s.frame_begin - 4) * H)        # halo frame fb-1 starts at (fb-4)H
+            assert s.need_hi == min(n, (s.frame_end + 3) * H)          # three OLA frames after the range
+            assert s.need_lo % H == 0 and s.frame_offset * H == s.need_lo
+        if w > 1:
+            assert sh[1].left_halo == N and sh[0].right_halo == 3 * H  # the seam payloads
+
+
+def _worker(rank, world, port, n, N, H, out):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        x = torch.arange(n, dtype=torch.float32)
+        shards = D.plan_time_shards(n, N, H, world)
+        s = shards[rank]
+        win = D.exchange_seam_samples(x[s.own_lo:s.own_hi].clone(), s, world)
+        ok_seam = torch.equal(win, x[s.need_lo:s.need_hi])
+        # exact uint32 phase carry: values near 2^32 must wrap
+        tot = torch.tensor([[4294967295, 5, 2 ** 31 + rank]], dtype=torch.int64) + rank
+        pre = D.exclusive_phase_prefix(tot, world, rank)
+        exp = torch.zeros_like(tot)
+        for r in range(rank):
+            exp = (exp + torch.tensor([[4294967295, 5, 2 ** 31 + r]], dtype=torch.int64) + r) & 0xFFFFFFFF
+        out[rank] = bool(ok_seam) and torch.equal(pre, exp)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_seam_exchange_and_phase_prefix_gloo(world):
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, 48000 * 3 + 77, 2048, 512, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)) and len(out) == world

@@ -1,0 +1,185 @@
+"""-m gpu: phase-vocoder path (K_A / scan / K_S) through the C ABI against the double-precision
+oracle (PV-spec v1; NOT IN REFERENCE -- parity unpinned by reference, self-consistency target).
+Tolerances (BASELINE.json north_star): output RMS <= 1e-4 absolute; peak bins bit-exact on every
+frame whose top-two magnitude margin exceeds 1e-5; f0 within 1e-3 Hz."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import signals as S  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def rms(a, b):
+    return float(np.sqrt(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2)))
+
+
+def ratio(semis):
+    import melonix_b200 as m
+    return m.semitone_ratio(semis)
+
+
+def check(g, o, tol=1e-4):
+    ok = o["margin"] > 1e-5
+    assert rms(g["y"], o["y"]) <= tol
+    assert np.array_equal(g["peak"][ok], o["peak"][ok])
+    assert np.abs(g["f0"][ok] - o["f0"][ok]).max() < 1e-3
+    return int((~ok).sum())
+
+
+def test_config2_full_pitch_shift(engine, oracle):
+    """BASELINE configs[1]: 60 s mono, 2048-FFT / 512-hop, +3 semitones."""
+    x = S.vibrato_tone(60.0, seed=1234)
+    engine.upload_tracks([x])
+    g = engine.pv_run(2048, 512, ratio(3.0))[0]
+    o = oracle.pv_run(x, 2048, 512, ratio(3.0))
+    assert g["peak"].size == 5625
+    excluded = check(g, o)
+    assert excluded == 0
+    assert rms(g["y"], o["y"]) < 1e-6          # what the kernels actually achieve
+
+
+@pytest.mark.parametrize("N", [512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("semis", [3.0, -4.0, 0.0, 12.0, -24.0])
+def test_sizes_and_ratios(engine, oracle, N, semis):
+    x = S.vibrato_tone(3.0, seed=N + int(semis))
+    engine.upload_tracks([x])
+    g = engine.pv_run(N, N // 4, ratio(semis))[0]
+    o = oracle.pv_run(x, N, N // 4, ratio(semis))
+    check(g, o)
+
+
+def test_golden_vectors(engine):
+    for name, N in (("pv_2048_p3.npz", 2048), ("pv_1024_m5.npz", 1024)):
+        gold = np.load(GOLD / name)
+        x = S.vibrato_tone(float(gold["seconds"]), seed=int(gold["seed"]))
+        engine.upload_tracks([x])
+        g = engine.pv_run(N, N // 4, float(gold["rate"]))[0]
+        ok = gold["margin"] > 1e-5
+        assert rms(g["y"], gold["y"]) <= 1e-4
+        assert np.array_equal(g["peak"][ok], gold["peak"][ok])
+
+
+def test_ragged_batch_silence_and_tiny_tracks(engine, oracle):
+    xs = [S.vibrato_tone(2.0, seed=1), S.vibrato_tone(1.37, seed=2, f_base=330.0), S.vibrato_tone(0.2, seed=3),
+          np.zeros(30000, np.float32),                                # digital silence: the |Z| gate
+          np.concatenate([np.zeros(9000, np.float32), S.vibrato_tone(0.5, seed=4), np.zeros(7000, np.float32)]),
+          S.vibrato_tone(0.004, seed=5),                              # shorter than one hop
+          np.full(1, 0.5, np.float32)]
+    engine.upload_tracks(xs)
+    r = ratio(3.0)
+    gs = engine.pv_run(2048, 512, r)
+    for x, g in zip(xs, gs):
+        o = oracle.pv_run(x, 2048, 512, r)
+        assert rms(g["y"], o["y"]) <= 1e-4
+        ok = o["margin"] > 1e-5
+        assert np.array_equal(g["peak"][ok], o["peak"][ok])
+    assert not gs[3]["y"].any()
+
+
+def test_identity_property_full_size(engine):
+    """Size-independent property at BASELINE's full track length (5 min): r = 1 reproduces the input
+    away from the two edges (PV-spec A.8)."""
+    x = S.vibrato_tone(300.0, seed=77)
+    engine.upload_tracks([x])
+    g = engine.pv_run(2048, 512, 1.0)[0]
+    i = slice(2048, x.size - 2048)
+    assert rms(g["y"][i], x[i]) < 2e-6
+    assert g["peak"].size == 28125
+
+
+def test_no_drift_on_stationary_tones(engine, oracle):
+    """A smooth per-frame phase error would grow linearly with time; the integer-turn phase
+    difference makes it telescope.  300 s of stationary partials: error flat from start to end."""
+    n = 300 * 48000
+    t = np.arange(n) / 48000.0
+    x = (0.3 * np.sin(2 * np.pi * 441.3 * t) + 0.15 * np.sin(2 * np.pi * 1237.7 * t + 0.3)
+         + 1e-4 * np.random.default_rng(5).standard_normal(n)).astype(np.float32)
+    engine.upload_tracks([x])
+    g = engine.pv_run(2048, 512, ratio(3.0))[0]
+    o = oracle.pv_run(x, 2048, 512, ratio(3.0))
+    seg = 5 * 48000
+    first, last = rms(g["y"][:seg], o["y"][:seg]), rms(g["y"][-seg:], o["y"][-seg:])
+    assert first < 1e-6 and last < 1e-6 and last < 3 * first + 1e-7
+    assert np.array_equal(g["peak"], o["peak"])
+
+
+def test_wave_tiling_and_chunking_are_bitwise_invisible(engine, monkeypatch):
+    xs = [S.vibrato_tone(6.0, seed=21), S.vibrato_tone(4.3, seed=22)]
+    engine.upload_tracks(xs)
+    r = ratio(-2.0)
+    a = engine.pv_run(2048, 512, r, wave_mib=-1)
+    b = engine.pv_run(2048, 512, r, wave_mib=1)
+    monkeypatch.setenv("MLX_PV_CHUNK", "24")
+    c = engine.pv_run(2048, 512, r, wave_mib=2)
+    for u, v, w in zip(a, b, c):
+        assert np.array_equal(u["y"], v["y"]) and np.array_equal(u["y"], w["y"])
+        assert np.array_equal(u["peak"], v["peak"]) and np.array_equal(u["f0"], w["f0"])
+
+
+def test_time_range_shards_equal_unsharded_bitwise(engine):
+    """S logical shards run one after the other on one GPU (seam exchange =
+    slicing, phase carry = prefix of the shard totals) must equal the unsharded result bit for bit."""
+    import torch
+    from melonix_b200 import dist as D
+    N, H = 4096, 1024
+    x = S.vibrato_tone(20.0, seed=31)
+    r = ratio(3.0)
+    engine.upload_tracks([x])
+    full = engine.pv_run(N, H, r)[0]
+    xd = torch.from_numpy(x).cuda()
+    engine.use_torch_stream()
+    for world in (2, 5):
+        shards = D.plan_time_shards(x.size, N, H, world)
+        carry = torch.zeros(N // 2 + 1, dtype=torch.int64, device="cuda")
+        y = np.zeros_like(x)
+        peak = np.zeros_like(full["peak"])
+        for s in shards:
+            win = xd[s.need_lo:s.need_hi].contiguous()
+            engine.upload_tracks_dev([win])
+            tot = torch.zeros(N // 2 + 1, dtype=torch.int32, device="cuda")
+            engine.pv_phase_totals_dev(N, H, r, [tot], frame_begin=s.local_frame_begin, frame_end=s.local_frame_end,
+                                       wave_mib=-1)
+            c32 = torch.where(carry >= 2 ** 31, carry - 2 ** 32, carry).to(torch.int32)
+            yd = torch.zeros_like(win)
+            pk = torch.zeros(D.num_frames(win.numel(), H), dtype=torch.int32, device="cuda")
+            engine.pv_run_dev(N, H, r, [yd], [pk], None, frame_begin=s.local_frame_begin,
+                              frame_end=s.local_frame_end, phase_in=[c32], wave_mib=-1)
+            torch.cuda.synchronize()
+            y[s.own_lo:s.own_hi] = yd[s.left_halo:s.left_halo + (s.own_hi - s.own_lo)].cpu().numpy()
+            peak[s.frame_begin:s.frame_end] = pk[s.local_frame_begin:s.local_frame_end].cpu().numpy()
+            carry = (carry + (tot.to(torch.int64) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        assert np.array_equal(y, full["y"]), f"world={world}"
+        assert np.array_equal(peak, full["peak"])
+
+
+def test_per_frame_rate_array(engine, oracle):
+    import torch
+    x = S.vibrato_tone(2.0, seed=41)
+    F = (x.size + 511) // 512
+    rates = (2.0 ** (np.linspace(-3, 5, F) / 12.0)).astype(np.float32)
+    engine.upload_tracks([x])
+    engine.use_torch_stream()
+    y = torch.zeros(x.size, dtype=torch.float32, device="cuda")
+    engine.pv_run_dev(2048, 512, 1.0, [y], rate_per_frame=[torch.from_numpy(rates).cuda()])
+    torch.cuda.synchronize()
+    o = oracle.pv_run(x, 2048, 512, 1.0, rate_per_frame=rates)
+    assert rms(y.cpu().numpy(), o["y"]) <= 1e-4
+
+
+def test_host_pipeline_equals_resident_run(engine):
+    xs = [S.vibrato_tone(3.0, seed=51), S.vibrato_tone(2.2, seed=52), S.vibrato_tone(0.7, seed=53)]
+    r = ratio(3.0)
+    engine.upload_tracks(xs)
+    a = engine.pv_run(2048, 512, r)
+    ys = [np.zeros_like(x) for x in xs]
+    pk = [np.zeros((x.size + 511) // 512, np.int32) for x in xs]
+    f0 = [np.zeros((x.size + 511) // 512, np.float32) for x in xs]
+    engine.pv_process_host(xs, 2048, 512, r, ys, pk, f0)
+    for u, y, p, f in zip(a, ys, pk, f0):
+        assert np.array_equal(u["y"], y) and np.array_equal(u["peak"], p) and np.array_equal(u["f0"], f)

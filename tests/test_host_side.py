@@ -1,0 +1,93 @@
+"""CPU tests of the product's host side: the device FFT's index arithmetic (sequential emulation),
+the C-ABI libraries' exported symbols, the host grain schedule against the oracle, and the loud
+failure when no GPU is present."""
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import signals as S  # noqa: E402
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_device_fft_emulated_on_host(tmp_path):
+    """melonix_b200/csrc/fft.cuh compiled by g++ with a sequential thread-group emulation."""
+    exe = tmp_path / "fft_emul"
+    gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    subprocess.run([gxx, "-std=c++17", "-O2", "-x", "c++", str(ROOT / "tests/host/fft_emul.cpp"), "-x", "c",
+                    str(ROOT / "oracle/fft64.c"), "-o", str(exe), "-lm"], check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from melonix_b200 import capi, hostlib
+    L = capi.lib()
+    syms = capi.declared_symbols()
+    assert len(syms) >= 20
+    assert [s for s in syms if not hasattr(L, s)] == []
+    H = hostlib.lib()
+    hs = hostlib.declared_symbols()
+    assert len(hs) == 6 and [s for s in hs if not hasattr(H, s)] == []
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import melonix_b200 as m
+    with pytest.raises(m.MlxError) as e:
+        m.Engine(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_host_grain_schedule_matches_oracle(oracle):
+    from melonix_b200 import hostlib as H
+    x = S.two_tone(6.0)
+    gs, gl = H.grain_segment(x)
+    ogs, ogl = oracle.grain_segment(x)
+    assert np.array_equal(gs, ogs) and np.array_equal(gl, ogl)
+    for mk in ([], [(10, 0, 0, 3.0), (x.size - 10, 0, 0, 3.0)], [(10, 0, 0, -7.0), (x.size - 10, 0, 0, -7.0)],
+               [(40000, 0, 0.5, 2.0), (120000, 0, -0.3, -1.5), (250000, 0, 0.0, 4.0)]):
+        s = H.export_schedule(x, 48000, mk, gs, gl)
+        o = oracle.grain_export(x, 48000, mk, ogs, ogl)
+        for k in ("gstart", "glen", "rate", "next"):
+            assert np.array_equal(s[k], o["schedule"][k]), k
+        assert np.array_equal(s["out_off"][:-1], o["schedule"]["out_off"])
+        assert s["out_off"][-1] + s["tail_zeros"] == o["pcm"].size
+        for t in (0.0, 0.37, 1.9, 5.5, 7.0):
+            assert H.time2sample(mk, 48000, t) == oracle.time2sample(mk, 48000, t)
+            assert H.time2pitchbend(mk, 48000, x.size, t) == oracle.time2pitchbend(mk, 48000, x.size, t)
+        for smp in (0, 1000, 100000, 260000):
+            assert H.sample2time(mk, 48000, smp) == oracle.sample2time(mk, 48000, smp)
+
+
+def test_grain_edge_cases(oracle):
+    from melonix_b200 import hostlib as H
+    for x in (np.zeros(0, np.float32), np.zeros(1200, np.float32), np.ones(5000, np.float32),
+              S.two_tone(0.05), -S.two_tone(0.2)):
+        gs, gl = H.grain_segment(x)
+        ogs, ogl = oracle.grain_segment(x)
+        assert np.array_equal(gs, ogs) and np.array_equal(gl, ogl)
+        s = H.export_schedule(x, 48000, [], gs, gl)
+        o = oracle.grain_export(x, 48000, [], ogs, ogl)
+        assert s["out_off"][-1] + s["tail_zeros"] == o["pcm"].size
+
+
+def test_bench_reference_arm_contract():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0

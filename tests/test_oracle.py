@@ -1,0 +1,148 @@
+"""CPU tests of the oracle (oracle/): pinned against the reference's own spec.cpp compiled
+unmodified (oracle/_ref), the analytic KATs of SURVEY.md section 4, an independent numpy
+restatement of the PV spec, and the committed golden vectors."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import signals as S  # noqa: E402
+from np_pv_reference import pv_numpy  # noqa: E402
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def test_fft_against_numpy(oracle):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(3000).astype(np.float32)
+    jobs = np.array([[1000, 1256], [-5, 100], [2900, 3100], [-3000, -100], [7000, 7256]], np.int32)
+    for N in (512, 1024, 4096):
+        got = oracle.spec_batch(x, N, jobs, nthreads=1)
+        for j, (a, b) in enumerate(jobs):
+            i = np.arange(b - N, b)
+            ok = (i >= 0) & (i < x.size)
+            xi = np.where(ok, x[np.clip(i, 0, x.size - 1)], 0).astype(np.float32)
+            w = np.where(i >= a, np.float32(1), np.exp(np.float32(-2.5e-4) * (a - i).astype(np.float32)).astype(np.float32))
+            ref = np.abs(np.fft.fft((w * xi).astype(np.float32).astype(np.float64)))[:N // 2] / N
+            assert np.abs(got[j] - ref).max() < 5e-8
+
+
+def test_kat1_spec_peak(oracle):
+    # analytic peak of the reference window
+    n = 200000
+    wav = (0.5 * np.sin(2 * np.pi * 300 * np.arange(n) / 32768)).astype(np.float32)
+    s = oracle.spec_batch(wav, 32768, np.array([[100000, 100375]], np.int32))[0]
+    assert s.size == 16384 and s.argmax() == 300
+    assert abs(float(s.max()) - 0.03340026) < 1e-7
+    a = 2.5e-4
+    W = 375 + np.exp(-a) * (1 - np.exp(-a * (32768 - 375))) / (1 - np.exp(-a))
+    assert abs(float(s.max()) - 0.25 * W / 32768) < 1e-4  # closed form is approximate (leakage)
+
+
+def test_kat2_spec_edges(oracle):
+    x = S.sine_sweep(0.2)
+    jobs = np.array([[-5000, 0], [-100, -1], [x.size + 1024, x.size + 1280]], np.int32)
+    assert not oracle.spec_batch(x, 1024, jobs).any()
+
+
+def test_restatement_equals_reference_spec_cpp(oracle):
+    """oracle/spec_ref.c vs the reference's own Spec class (spec.cpp compiled unmodified)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    x = S.vibrato_tone(1.0, seed=3)
+    jobs = np.array([[0, 375], [20000, 20375], [-200, 175], [x.size - 100, x.size + 275], [40000, 41000]], np.int32)
+    ref = oracle.ref_spec_run(x, jobs)
+    got = oracle.spec_batch(x, 32768, jobs, nthreads=2)
+    assert np.array_equal(ref, got)
+
+
+def test_golden_spec(oracle):
+    g = np.load(GOLD / "spec_ref_geometry.npz")
+    n = int(g["n"])
+    kat = (0.5 * np.sin(2 * np.pi * 300 * np.arange(n) / 32768)).astype(np.float32)
+    assert np.array_equal(oracle.spec_batch(kat, 32768, g["jobs"]), g["out"])  # golden = reference output
+    g = np.load(GOLD / "spec_cfg1.npz")
+    x = S.sine_sweep(float(g["seconds"]))
+    assert np.array_equal(oracle.spec_batch(x, 1024, g["jobs"]), g["out"])
+
+
+@pytest.mark.parametrize("N,semis", [(1024, 0.0), (2048, 3.0), (512, -5.0), (4096, -12.0), (512, 11.0)])
+def test_pv_oracle_against_numpy_restatement(oracle, N, semis):
+    fs = 48000
+    t = np.arange(fs // 3) / fs
+    rng = np.random.default_rng(3)
+    x = (0.4 * np.sin(2 * np.pi * 440 * t) + 0.1 * np.sin(2 * np.pi * 1230 * t + 1) + 1e-3 * rng.standard_normal(t.size)).astype(np.float32)
+    r = np.float32(2.0) ** (np.float32(semis) / np.float32(12.0))
+    o = oracle.pv_run(x, N, N // 4, r)
+    y, pk, f0 = pv_numpy(x, N, N // 4, r)
+    assert np.sqrt(np.mean((o["y"].astype(np.float64) - y) ** 2)) < 1e-9
+    assert np.array_equal(pk, o["peak"])
+    assert np.abs(f0 - o["f0"]).max() < 1e-3
+
+
+def test_pv_identity_and_pitch(oracle):
+    fs = 48000
+    x = (0.5 * np.sin(2 * np.pi * 440 * np.arange(fs) / fs)).astype(np.float32)
+    o = oracle.pv_run(x, 2048, 512, 1.0)
+    i = slice(2048, x.size - 2048)
+    assert np.sqrt(np.mean((o["y"][i] - x[i]) ** 2)) < 1e-6          # r = 1 reproduces the input
+    assert set(o["peak"][8:-8]) == {19}                               # 440 Hz -> bin 19 at 2048/48k
+    assert abs(np.median(o["f0"][8:-8]) - 440.0) < 0.01
+    r = np.float32(2.0) ** (np.float32(3.0) / np.float32(12.0))
+    y = oracle.pv_run(x, 2048, 512, r)["y"].astype(np.float64)
+    spec = np.abs(np.fft.rfft(y[8192:8192 + 32768] * np.hanning(32768)))
+    assert abs(spec.argmax() * fs / 32768 - 440 * 2 ** 0.25) < 3.0     # shifted to ~523 Hz
+
+
+def test_golden_pv(oracle):
+    for name, N in (("pv_2048_p3.npz", 2048), ("pv_1024_m5.npz", 1024)):
+        g = np.load(GOLD / name)
+        x = S.vibrato_tone(float(g["seconds"]), seed=int(g["seed"]))
+        o = oracle.pv_run(x, N, N // 4, float(g["rate"]))
+        assert np.array_equal(o["y"], g["y"]) and np.array_equal(o["peak"], g["peak"])
+        assert np.allclose(o["f0"], g["f0"], rtol=0, atol=1e-4)
+
+
+def test_kat4_kat5_grains(oracle):
+    x = S.two_tone(20.0)
+    gs, gl = oracle.grain_segment(x)
+    assert gs.size == 628 and gl.min() >= 1519 and gl.max() <= 1528   # SURVEY.md KAT-4 probe
+    e = oracle.grain_export(x, 48000, [], gs, gl)
+    total = int(gl.sum())
+    assert e["pcm"].size == total + 1500
+    assert np.array_equal(e["pcm"][:total], x[:total]) and not e["pcm"][total:].any()
+    for semis, steps in ((3.0, 746), (-3.0, 528)):                    # KAT-5: duration preserved
+        mk = [(10, 0, 0, semis), (x.size - 10, 0, 0, semis)]
+        e = oracle.grain_export(x, 48000, mk, gs, gl)
+        assert abs(e["pcm"].size - x.size) < 2300
+        assert e["schedule"]["rate"].size == steps
+
+
+def test_golden_grain_and_colormap(oracle):
+    g = np.load(GOLD / "grain_p3.npz")
+    x = S.two_tone(float(g["seconds"]))
+    gs, gl = oracle.grain_segment(x)
+    assert np.array_equal(gs, g["g_start"]) and np.array_equal(gl, g["g_len"])
+    e = oracle.grain_export(x, 48000, [(10, 0, 0, 3.0), (x.size - 10, 0, 0, 3.0)], gs, gl)
+    assert np.array_equal(e["pcm16"], g["pcm16"]) and np.array_equal(e["pcm"], g["pcm"])
+    c = np.load(GOLD / "colormap.npz")
+    assert np.array_equal(oracle.colormap(c["v"], float(c["k"])), c["rgb"])
+
+
+def test_colormap_matches_numpy_restatement(oracle):
+    v = np.linspace(0, 3, 997).astype(np.float32)
+    k = np.float32(100.0)
+    tmp = np.clip(v * k, np.float32(0), np.float32(255)).astype(np.float32)
+    exp = np.zeros((v.size, 3), np.uint8)
+    for i, t in enumerate(tmp):
+        if t < 85:
+            exp[i] = (int(t), 0, 0)
+        elif t < 170:
+            a = float(np.float32(np.float32(t - np.float32(85)) / np.float32(85))) * 3.141592 / 2
+            exp[i] = (int(float(t) * np.cos(a)), int(float(t) * np.sin(a)), 0)
+        else:
+            lk = int(np.float32(np.float32(t - np.float32(170)) * np.float32(3)))
+            exp[i] = (lk, int(t), lk)
+    assert np.array_equal(oracle.colormap(v, float(k)), exp)
