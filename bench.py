@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tracks", type=int, default=64, help="tracks per GPU")
     ap.add_argument("--seconds", type=float, default=300.0, help="seconds per track")
-    ap.add_argument("--wave-mib", type=int, default=0, help="L2-tiling budget (0 = library default, <0 = off)")
+    ap.add_argument("--wave-mib", type=int, default=0, help="intermediate-stage budget in MiB (0 = library default: one wave)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -105,8 +105,9 @@ typedef struct {
   /* accumulated synthesis phase carried in from earlier frames of the same track: per-track
    * device arrays of fftN/2+1 uint32 (NULL, or entries NULL -> 0).                              */
   const uint32_t *const *phase_in_dev;
-  /* L2-tiling budget in MiB for the analysis->synthesis intermediates; 0 = library default,
-   * <0 = one wave over the whole range.                                                          */
+  /* budget in MiB for the analysis->synthesis intermediates (8*(fftN/2+32) bytes per frame):
+   * >0 tiles the frame range into waves of that size (e.g. to keep them in L2); <0 = one wave over
+   * the whole range; 0 = library default (one wave unless that exceeds 1/4 of device memory).     */
   int wave_mib;
 } mlx_pv_params;
 

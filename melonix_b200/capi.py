@@ -11,7 +11,10 @@ import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libmelonix_b200.so"
+import os
+
+# MELONIX_B200_LIB: alternative build of the same library (kernel tuning experiments only)
+LIB_PATH = Path(os.environ.get("MELONIX_B200_LIB", _PKG / "libmelonix_b200.so"))
 HEADER_PATH = _PKG.parent / "include" / "melonix_gpu.h"
 
 MLX_OK = 0

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -99,21 +100,35 @@ struct mlx_ctx {
   DevBuf out_wav, out_peak, out_f0;  // device results for the host-pointer entry points
   DevBuf jobs, spec_out, spec_rgb;
   DevBuf g_i32a, g_i32b, g_f32a, g_f32b, g_i64, g_out, g_out16;
-  void* pinned = nullptr;
-  size_t pinned_bytes = 0;
+  // pinned staging ring for per-call descriptors / tables: a slot is reused only after the copies
+  // that read it have completed (event), so launches never wait on the host.
+  struct Slot {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t done = nullptr;
+  };
+  Slot slots[8];
+  int next_slot = 0;
 
   const float* track_ptr(int t) const { return static_cast<const float*>(track_buf.p) + tracks[t].offset; }
 };
 
 namespace {
 
-int reserve_pinned(mlx_ctx* c, size_t bytes) {
-  if (bytes <= c->pinned_bytes) return MLX_OK;
-  if (c->pinned) cudaFreeHost(c->pinned);
-  c->pinned = nullptr;
-  c->pinned_bytes = 0;
-  CK(cudaMallocHost(&c->pinned, bytes));
-  c->pinned_bytes = bytes;
+// next staging slot of at least `bytes` (waits only if the GPU is 8 calls behind)
+int acquire_slot(mlx_ctx* c, size_t bytes, mlx_ctx::Slot** out) {
+  mlx_ctx::Slot& s = c->slots[c->next_slot];
+  c->next_slot = (c->next_slot + 1) % 8;
+  if (!s.done) CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  CK(cudaEventSynchronize(s.done));
+  if (s.bytes < bytes) {
+    if (s.p) cudaFreeHost(s.p);
+    s.p = nullptr;
+    s.bytes = 0;
+    CK(cudaMallocHost(&s.p, bytes));
+    s.bytes = bytes;
+  }
+  *out = &s;
   return MLX_OK;
 }
 
@@ -236,30 +251,98 @@ int pv_validate(mlx_ctx* c, const mlx_pv_params* p, PvPlan* pl) {
   while (pl->G * m - 3 < 1) ++m;
   pl->CA = pl->G * m - 1;
   pl->CS = pl->G * m - 3;
-  // wave size
-  int mib = p->wave_mib;
-  if (mib == 0) {
-    mib = 96;
-    if (const char* e = getenv("MLX_PV_WAVE_MIB")) mib = atoi(e);
+  // wave size.  Default: one wave over the whole range (the intermediates stream through HBM, which
+  // has >90 % headroom on this compute-bound path) unless that would take more than a quarter of the
+  // device memory; an explicit budget tiles the range so that a wave's intermediates stay in L2.
+  const double per_frame = (double)c->tracks.size() * pl->NBP * 8.0;
+  double budget = -1.0;
+  if (p->wave_mib > 0) budget = (double)p->wave_mib * 1048576.0;
+  if (p->wave_mib == 0) {
+    if (const char* e = getenv("MLX_PV_WAVE_MIB")) {
+      if (atoi(e) > 0) budget = (double)atoi(e) * 1048576.0;
+    } else if (per_frame * (double)(span + 3) > 0.25 * (double)c->total_mem) {
+      budget = 0.25 * (double)c->total_mem;
+    }
   }
-  if (mib < 0) {
+  if (budget < 0) {
     pl->wave_frames = span;
   } else {
-    const double per_frame = (double)c->tracks.size() * pl->NBP * 8.0;
-    int64_t wf = (int64_t)((double)mib * 1048576.0 / per_frame) - 3;
+    int64_t wf = (int64_t)(budget / per_frame) - 3;
     wf = std::max<int64_t>(wf, pl->CA);
     pl->wave_frames = std::min<int64_t>(wf, span);
   }
   return MLX_OK;
 }
 
-// Runs waves of K_A -> scan (-> K_S) over frames [fb, fe) of all uploaded tracks.
-int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth, float* const* out_wav,
-               int32_t* const* out_peak, float* const* out_f0, uint32_t* const* totals_dev) {
+// Stages everything a run needs on the device BEFORE any bulk copy is queued: track descriptors,
+// the bin-shift table of the constant rate, zeroed / carried-in phase.  (Small H2D copies issued
+// later would queue behind gigabytes of uploads on the single H2D copy engine.)
+struct PvPrepared {
+  const PvTrack* tdev = nullptr;  // [ntracks]
+  uint32_t* carry = nullptr;      // [ntracks][NBP]
   Tables* tb = nullptr;
-  int rc = ensure_tables(c, pl.N, true, &tb);
-  if (rc) return rc;
+};
+
+int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* const* out_wav,
+               int32_t* const* out_peak, float* const* out_f0, PvPrepared* out) {
   const int nt = (int)c->tracks.size();
+  const int H = fftN / 4, NBP = pv_nbp(fftN), NC = fftN / 2, NB = NC + 1;
+  int rc = ensure_tables(c, fftN, true, &out->tb);
+  if (rc) return rc;
+  CK(c->track_desc.reserve(sizeof(PvTrack) * nt));
+  CK(c->gk.reserve(sizeof(uint32_t) * NBP));
+  CK(c->carry.reserve(sizeof(uint32_t) * nt * NBP));
+  const size_t desc_bytes = (sizeof(PvTrack) * nt + 15) & ~size_t(15);
+  mlx_ctx::Slot* slot = nullptr;
+  rc = acquire_slot(c, desc_bytes + sizeof(uint32_t) * NBP, &slot);
+  if (rc) return rc;
+  PvTrack* desc = static_cast<PvTrack*>(slot->p);
+  uint32_t* gk = reinterpret_cast<uint32_t*>(static_cast<char*>(slot->p) + desc_bytes);
+  for (int t = 0; t < nt; ++t) {
+    desc[t].x = c->track_ptr(t);
+    desc[t].n = c->tracks[t].n;
+    desc[t].F = num_frames(c->tracks[t].n, H);
+    desc[t].out = (synth && out_wav) ? out_wav[t] : nullptr;
+    desc[t].peak = out_peak ? out_peak[t] : nullptr;
+    desc[t].f0 = out_f0 ? out_f0[t] : nullptr;
+    desc[t].rate_pf = p->rate_per_frame_dev ? p->rate_per_frame_dev[t] : nullptr;
+  }
+  // bin-shift table for the constant rate (PV-spec A.5): one float multiply per bin, as the spec says
+  {
+    for (int j = 0; j < NBP; ++j) gk[j] = 1u;  // klo = 1, khi = 0: empty
+    std::vector<int> klo(NB, 1), khi(NB, 0);
+    const float r = p->rate;
+    for (int k = 0; k < NB; ++k) {
+      const float tf = (float)k * r;
+      const int j = (int)std::trunc(tf);
+      if (j < 0 || j >= NB) continue;
+      if (klo[j] > khi[j]) klo[j] = k;
+      khi[j] = k;
+    }
+    for (int j = 0; j < NB; ++j)
+      if (klo[j] <= khi[j]) gk[j] = (uint32_t)klo[j] | ((uint32_t)khi[j] << 16);
+  }
+  CK(cudaMemcpyAsync(c->track_desc.p, desc, sizeof(PvTrack) * nt, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->gk.p, gk, sizeof(uint32_t) * NBP, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(slot->done, c->stream));
+  CK(cudaMemsetAsync(c->carry.p, 0, sizeof(uint32_t) * nt * NBP, c->stream));
+  if (p->phase_in_dev) {
+    for (int t = 0; t < nt; ++t)
+      if (p->phase_in_dev[t])
+        CK(cudaMemcpyAsync(static_cast<uint32_t*>(c->carry.p) + (size_t)t * NBP, p->phase_in_dev[t],
+                           sizeof(uint32_t) * NB, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  out->tdev = static_cast<const PvTrack*>(c->track_desc.p);
+  out->carry = static_cast<uint32_t*>(c->carry.p);
+  return MLX_OK;
+}
+
+// Launches waves of K_A -> scan (-> K_S) over frames [fb, fe) of `nt` prepared tracks starting at
+// `first`.  Issues kernels only (plus optional D2D copies of the phase totals): nothing here touches
+// the H2D copy engine.
+int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrepared& pr, int first, int nt,
+              bool synth, uint32_t* const* totals_dev) {
+  Tables* tb = pr.tb;
   const size_t rows = (size_t)pl.wave_frames + 3;
   const size_t nchunksA_max = (size_t)((pl.wave_frames + 3 + pl.CA - 1) / pl.CA);
   CK(c->smag.reserve(sizeof(float) * nt * rows * pl.NBP));
@@ -267,65 +350,15 @@ int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth,
   CK(c->tot.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
   CK(c->totc.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
   CK(c->pre.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
-  CK(c->carry.reserve(sizeof(uint32_t) * nt * pl.NBP));
-  CK(c->track_desc.reserve(sizeof(PvTrack) * nt));
-  rc = reserve_pinned(c, sizeof(PvTrack) * nt);
-  if (rc) return rc;
-
-  // the previous call's descriptors may still be in flight from pinned memory
-  CK(cudaStreamSynchronize(c->stream));
-  PvTrack* desc = static_cast<PvTrack*>(c->pinned);
-  for (int t = 0; t < nt; ++t) {
-    desc[t].x = c->track_ptr(t);
-    desc[t].n = c->tracks[t].n;
-    desc[t].F = num_frames(c->tracks[t].n, pl.H);
-    desc[t].out = (synth && out_wav) ? out_wav[t] : nullptr;
-    desc[t].peak = out_peak ? out_peak[t] : nullptr;
-    desc[t].f0 = out_f0 ? out_f0[t] : nullptr;
-    desc[t].rate_pf = p->rate_per_frame_dev ? p->rate_per_frame_dev[t] : nullptr;
-  }
-  CK(cudaMemcpyAsync(c->track_desc.p, desc, sizeof(PvTrack) * nt, cudaMemcpyHostToDevice, c->stream));
-
-  // carry-in phase
-  CK(cudaMemsetAsync(c->carry.p, 0, sizeof(uint32_t) * nt * pl.NBP, c->stream));
-  if (p->phase_in_dev) {
-    for (int t = 0; t < nt; ++t)
-      if (p->phase_in_dev[t])
-        CK(cudaMemcpyAsync(static_cast<uint32_t*>(c->carry.p) + (size_t)t * pl.NBP, p->phase_in_dev[t],
-                           sizeof(uint32_t) * (pl.N / 2 + 1), cudaMemcpyDeviceToDevice, c->stream));
-  }
 
   PvTables pt{static_cast<const cplx<double>*>(tb->tw_d.p), static_cast<const cplx<double>*>(tb->twr_d.p),
               static_cast<const cplx<float>*>(tb->tw_f.p),  static_cast<const cplx<float>*>(tb->twr_f.p),
               static_cast<const float*>(tb->win.p),         static_cast<const double*>(tb->win_d.p),
               static_cast<const float*>(tb->wsyn.p)};
-  PvScratch sc{static_cast<float*>(c->smag.p), static_cast<uint32_t*>(c->lacc.p), static_cast<uint32_t*>(c->tot.p),
-               static_cast<uint32_t*>(c->totc.p), static_cast<uint32_t*>(c->pre.p), static_cast<uint32_t*>(c->carry.p)};
-  const PvTrack* tdev = static_cast<const PvTrack*>(c->track_desc.p);
-
-  // bin-shift table for the constant rate (PV-spec A.5): one float multiply per bin, as the spec says
-  {
-    const int NC = pl.N / 2, NB = NC + 1;
-    std::vector<uint32_t> gk(pl.NBP, 1u);
-    std::vector<int> klo(NB, 1), khi(NB, 0);
-    const float r = p->rate;
-    for (int k = 0; k < NB; ++k) {
-      const float tf = (float)k * r;  // one float multiply, as the spec says
-      const int j = (int)std::trunc(tf);
-      if (j < 0 || j >= NB) continue;
-      if (klo[j] > khi[j]) klo[j] = k;
-      khi[j] = k;
-    }
-    for (int j = 0; j < NB; ++j) {
-      if (klo[j] <= khi[j]) {
-        gk[j] = (uint32_t)klo[j] | ((uint32_t)khi[j] << 16);
-      } else {
-        gk[j] = 1u;
-      }
-    }
-    CK(c->gk.reserve(sizeof(uint32_t) * pl.NBP));
-    CK(cudaMemcpyAsync(c->gk.p, gk.data(), sizeof(uint32_t) * pl.NBP, cudaMemcpyHostToDevice, c->stream));
-  }
+  PvScratch sc{static_cast<float*>(c->smag.p),    static_cast<uint32_t*>(c->lacc.p), static_cast<uint32_t*>(c->tot.p),
+               static_cast<uint32_t*>(c->totc.p), static_cast<uint32_t*>(c->pre.p),
+               pr.carry + (size_t)first * pl.NBP};
+  const PvTrack* tdev = pr.tdev + first;
 
   int kmin = (int)std::ceil(50.0 * pl.N / p->sample_rate), kmax = (int)std::floor(2000.0 * pl.N / p->sample_rate);
   kmin = std::max(kmin, 1);
@@ -362,10 +395,19 @@ int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth,
   if (totals_dev) {
     for (int t = 0; t < nt; ++t)
       if (totals_dev[t])
-        CK(cudaMemcpyAsync(totals_dev[t], static_cast<uint32_t*>(c->carry.p) + (size_t)t * pl.NBP,
-                           sizeof(uint32_t) * (pl.N / 2 + 1), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(totals_dev[t], sc.carry + (size_t)t * pl.NBP, sizeof(uint32_t) * (pl.N / 2 + 1),
+                           cudaMemcpyDeviceToDevice, c->stream));
   }
   return MLX_OK;
+}
+
+// prepare + launch over all uploaded tracks
+int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth, float* const* out_wav,
+               int32_t* const* out_peak, float* const* out_f0, uint32_t* const* totals_dev) {
+  PvPrepared pr;
+  int rc = pv_prepare(c, p, pl.N, synth, out_wav, out_peak, out_f0, &pr);
+  if (rc) return rc;
+  return pv_launch(c, p, pl, pr, 0, (int)c->tracks.size(), synth, totals_dev);
 }
 
 }  // namespace
@@ -415,7 +457,10 @@ void mlx_destroy(mlx_ctx* c) {
                       &kv.second.win_d, &kv.second.wsyn})
       b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
-  if (c->pinned) cudaFreeHost(c->pinned);
+  for (auto& s : c->slots) {
+    if (s.p) cudaFreeHost(s.p);
+    if (s.done) cudaEventDestroy(s.done);
+  }
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   delete c;
@@ -649,24 +694,59 @@ int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* 
   CK(cudaSetDevice(c->device));
   int rc = layout_tracks(c, n, ntracks);
   if (rc) return rc;
-  std::vector<Track> all = c->tracks;  // the pipeline runs the kernels one track at a time
+  const std::vector<Track> all = c->tracks;
+  const int H = p->hop;
   std::vector<size_t> woff(ntracks + 1, 0), foff(ntracks + 1, 0);
   for (int t = 0; t < ntracks; ++t) {
     woff[t + 1] = woff[t] + (((size_t)n[t] + 31) & ~size_t(31));
-    foff[t + 1] = foff[t] + (((size_t)num_frames(n[t], p->hop) + 31) & ~size_t(31));
+    foff[t + 1] = foff[t] + (((size_t)num_frames(n[t], H) + 31) & ~size_t(31));
   }
   CK(c->out_wav.reserve(sizeof(float) * std::max<size_t>(woff[ntracks], 1)));
   CK(c->out_peak.reserve(sizeof(int32_t) * std::max<size_t>(foff[ntracks], 1)));
   CK(c->out_f0.reserve(sizeof(float) * std::max<size_t>(foff[ntracks], 1)));
+  std::vector<float*> dw(ntracks, nullptr), df(ntracks, nullptr);
+  std::vector<int32_t*> dp(ntracks, nullptr);
+  for (int t = 0; t < ntracks; ++t) {
+    if (out_wav && out_wav[t]) dw[t] = static_cast<float*>(c->out_wav.p) + woff[t];
+    if (out_peak && out_peak[t]) dp[t] = static_cast<int32_t*>(c->out_peak.p) + foff[t];
+    if (out_f0 && out_f0[t]) df[t] = static_cast<float*>(c->out_f0.p) + foff[t];
+  }
+  // validate once (sizes, ratio) and stage descriptors / table / phase for ALL tracks up front
+  PvPlan pl_all{};
+  rc = pv_validate(c, p, &pl_all);
+  if (rc) return rc;
+  PvPrepared pr;
+  rc = pv_prepare(c, p, p->fftN, true, dw.data(), dp.data(), df.data(), &pr);
+  if (rc) return rc;
+  // scratch for the largest single track, allocated before the pipeline starts
+  {
+    int64_t nmax = 0;
+    for (int t = 0; t < ntracks; ++t) nmax = std::max<int64_t>(nmax, n[t]);
+    c->tracks.assign(1, Track{0, nmax});
+    PvPlan pl1{};
+    rc = pv_validate(c, p, &pl1);
+    c->tracks = all;
+    if (rc) return rc;
+    const size_t rows = (size_t)pl1.wave_frames + 3, nch = (size_t)((pl1.wave_frames + 3 + pl1.CA - 1) / pl1.CA);
+    CK(c->smag.reserve(sizeof(float) * rows * pl1.NBP));
+    CK(c->lacc.reserve(sizeof(uint32_t) * rows * pl1.NBP));
+    CK(c->tot.reserve(sizeof(uint32_t) * nch * pl1.NBP));
+    CK(c->totc.reserve(sizeof(uint32_t) * nch * pl1.NBP));
+    CK(c->pre.reserve(sizeof(uint32_t) * nch * pl1.NBP));
+  }
   std::vector<cudaEvent_t> ev_in(ntracks), ev_done(ntracks);
   for (int t = 0; t < ntracks; ++t) {
     cudaEventCreateWithFlags(&ev_in[t], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev_done[t], cudaEventDisableTiming);
   }
   cudaEvent_t ev_zero;
-  cudaEventCreateWithFlags(&ev_zero, cudaEventDisableTiming);
-  cudaEventRecord(ev_zero, c->stream);  // padding memset (layout_tracks) precedes the uploads
+  cudaEventCreate(&ev_zero);
+  cudaEventRecord(ev_zero, c->stream);  // padding memset + staging copies precede the uploads
   cudaStreamWaitEvent(c->s_in, ev_zero, 0);
+  const bool trace = getenv("MLX_TRACE") != nullptr;  // development aid: pipeline timeline on stderr
+  cudaEvent_t tr_in_end = nullptr, tr_k_first = nullptr, tr_k_last = nullptr, tr_out_first = nullptr, tr_out_last = nullptr;
+  if (trace)
+    for (cudaEvent_t* e : {&tr_in_end, &tr_k_first, &tr_k_last, &tr_out_first, &tr_out_last}) cudaEventCreate(e);
   int result = MLX_OK;
   for (int t = 0; t < ntracks && result == MLX_OK; ++t) {
     if (n[t] > 0 &&
@@ -675,27 +755,40 @@ int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* 
       result = fail(MLX_ERR_CUDA, "H2D copy failed");
     cudaEventRecord(ev_in[t], c->s_in);
   }
+  if (trace) cudaEventRecord(tr_in_end, c->s_in);
   for (int t = 0; t < ntracks && result == MLX_OK; ++t) {
     cudaStreamWaitEvent(c->stream, ev_in[t], 0);
-    c->tracks.assign(1, all[t]);
+    c->tracks.assign(1, all[t]);  // plan (chunk sizes) for this track alone; kernels only from here on
     PvPlan pl{};
     result = pv_validate(c, p, &pl);
     if (result) break;
-    float* dw = (out_wav && out_wav[t]) ? static_cast<float*>(c->out_wav.p) + woff[t] : nullptr;
-    int32_t* dp = (out_peak && out_peak[t]) ? static_cast<int32_t*>(c->out_peak.p) + foff[t] : nullptr;
-    float* df = (out_f0 && out_f0[t]) ? static_cast<float*>(c->out_f0.p) + foff[t] : nullptr;
-    result = pv_execute(c, p, pl, true, &dw, &dp, &df, nullptr);
+    result = pv_launch(c, p, pl, pr, t, 1, true, nullptr);
     if (result) break;
     cudaEventRecord(ev_done[t], c->stream);
+    if (trace && t == 0) cudaEventRecord(tr_k_first, c->stream);
+    if (trace && t == ntracks - 1) cudaEventRecord(tr_k_last, c->stream);
     cudaStreamWaitEvent(c->s_out, ev_done[t], 0);
-    const int64_t F = num_frames(n[t], p->hop);
-    if (dw && n[t] > 0) cudaMemcpyAsync(out_wav[t], dw, sizeof(float) * n[t], cudaMemcpyDeviceToHost, c->s_out);
-    if (dp && F > 0) cudaMemcpyAsync(out_peak[t], dp, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, c->s_out);
-    if (df && F > 0) cudaMemcpyAsync(out_f0[t], df, sizeof(float) * F, cudaMemcpyDeviceToHost, c->s_out);
+    const int64_t F = num_frames(n[t], H);
+    if (dw[t] && n[t] > 0) cudaMemcpyAsync(out_wav[t], dw[t], sizeof(float) * n[t], cudaMemcpyDeviceToHost, c->s_out);
+    if (dp[t] && F > 0) cudaMemcpyAsync(out_peak[t], dp[t], sizeof(int32_t) * F, cudaMemcpyDeviceToHost, c->s_out);
+    if (df[t] && F > 0) cudaMemcpyAsync(out_f0[t], df[t], sizeof(float) * F, cudaMemcpyDeviceToHost, c->s_out);
+    if (trace && t == 0) cudaEventRecord(tr_out_first, c->s_out);
+    if (trace && t == ntracks - 1) cudaEventRecord(tr_out_last, c->s_out);
   }
   c->tracks = all;
   cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_out),
               e3 = cudaStreamSynchronize(c->s_in);
+  if (trace && result == MLX_OK) {
+    float a = 0, b = 0, d = 0, e = 0, f = 0;
+    cudaEventElapsedTime(&a, ev_zero, tr_in_end);
+    cudaEventElapsedTime(&b, ev_zero, tr_k_first);
+    cudaEventElapsedTime(&d, ev_zero, tr_k_last);
+    cudaEventElapsedTime(&e, ev_zero, tr_out_first);
+    cudaEventElapsedTime(&f, ev_zero, tr_out_last);
+    fprintf(stderr, "[mlx trace] ms since start: last H2D done %.1f | kernels of track 0 done %.1f, last track %.1f | "
+                    "D2H of track 0 done %.1f, last %.1f\n", a, b, d, e, f);
+    for (cudaEvent_t ev : {tr_in_end, tr_k_first, tr_k_last, tr_out_first, tr_out_last}) cudaEventDestroy(ev);
+  }
   for (int t = 0; t < ntracks; ++t) {
     cudaEventDestroy(ev_in[t]);
     cudaEventDestroy(ev_done[t]);

@@ -26,7 +26,17 @@
 #include "fft.cuh"
 #include "kernels.h"
 
+#ifndef MLX_UNROLL_PAIR
+#define MLX_UNROLL_PAIR 2
+#endif
+#ifndef MLX_UNROLL_GATHER
+#define MLX_UNROLL_GATHER 2
+#endif
+
 namespace mlx {
+
+constexpr int kUnrollPair = MLX_UNROLL_PAIR;      // frames of the pair phase processed together (ILP)
+constexpr int kUnrollGather = MLX_UNROLL_GATHER;  // frames of the gather phase processed together
 
 // ------------------------------------------------------------------------------------------------
 template <int N, int G>
@@ -326,7 +336,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     __syncthreads();
 
     // ---- pair phase: X[k], X[NC-k] from Z; phase advance against the previous frame
-#pragma unroll 1
+#pragma unroll(kUnrollPair)
     for (int gg = 0; gg < G; ++gg) {
       const long long ff = f_first + gg;
       if (ff >= b) break;
@@ -388,7 +398,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     __syncthreads();
 
     // ---- gather phase: bin shift, exact phase increment, chunk-local scan, spill to HBM
-#pragma unroll 1
+#pragma unroll(kUnrollGather)
     for (int gg = (bi == 0 ? 1 : 0); gg < G; ++gg) {
       const long long ff = f_first + gg;
       if (ff >= b) break;
@@ -480,20 +490,47 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 }
 
 // ------------------------------------------------------------------------------------------------
-// exclusive scan over chunk totals, one thread per (track, bin)
-__global__ void pv_scan_kernel(int nb, int nbp, int nchunks, const PvScratch sc) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nb) return;
+// exclusive scan over the chunk totals of one wave.  Block = 32 bins x 8 chunk segments; every
+// thread first reduces its segment (independent loads), the segment sums are combined through
+// shared memory, then the segment is rescanned to emit the prefixes.
+constexpr int kScanSeg = 8;
+__global__ void __launch_bounds__(32 * kScanSeg)
+pv_scan_kernel(int nb, int nbp, int nchunks, const PvScratch sc) {
+  __shared__ uint32_t s_all[kScanSeg][32], s_cnt[kScanSeg][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   const size_t tr = blockIdx.y;
-  const uint32_t carry = sc.carry[tr * nbp + j];
-  uint32_t run = carry, counted = carry;
-  for (int c = 0; c < nchunks; ++c) {
-    const size_t i = (tr * nchunks + c) * nbp + j;
-    sc.pre[i] = run;
-    run += sc.tot[i];
-    counted += sc.totc[i];
+  const int len = (nchunks + kScanSeg - 1) / kScanSeg;
+  const int c0 = min(seg * len, nchunks), c1 = min(c0 + len, nchunks);
+  const uint32_t* __restrict__ tot = sc.tot + tr * nchunks * (size_t)nbp;
+  const uint32_t* __restrict__ totc = sc.totc + tr * nchunks * (size_t)nbp;
+  uint32_t* __restrict__ pre = sc.pre + tr * nchunks * (size_t)nbp;
+  uint32_t sum = 0u, sumc = 0u;
+  if (j < nb) {
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) {
+      sum += __ldg(tot + (size_t)c * nbp + j);
+      sumc += __ldg(totc + (size_t)c * nbp + j);
+    }
   }
-  sc.carry[tr * nbp + j] = counted;
+  s_all[seg][lane] = sum;
+  s_cnt[seg][lane] = sumc;
+  __syncthreads();
+  if (j >= nb) return;
+  const uint32_t carry = sc.carry[tr * nbp + j];
+  uint32_t run = carry;
+  for (int q = 0; q < seg; ++q) run += s_all[q][lane];
+#pragma unroll 4
+  for (int c = c0; c < c1; ++c) {
+    const uint32_t t = __ldg(tot + (size_t)c * nbp + j);
+    pre[(size_t)c * nbp + j] = run;
+    run += t;
+  }
+  if (seg == 0) {
+    uint32_t counted = carry;
+    for (int q = 0; q < kScanSeg; ++q) counted += s_cnt[q][lane];
+    sc.carry[tr * nbp + j] = counted;  // phase at the start of the next wave
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -753,8 +790,8 @@ cudaError_t launch_pv_analyze(int fftN, const PvTrack* tracks, int ntracks, cons
 
 cudaError_t launch_pv_scan(int fftN, int ntracks, const PvWave& wv, const PvScratch& sc, cudaStream_t st) {
   const int nb = fftN / 2 + 1;
-  dim3 grid((nb + 255) / 256, ntracks);
-  pv_scan_kernel<<<grid, 256, 0, st>>>(nb, pv_nbp(fftN), wv.nchunksA, sc);
+  dim3 grid((nb + 31) / 32, ntracks);
+  pv_scan_kernel<<<grid, 32 * kScanSeg, 0, st>>>(nb, pv_nbp(fftN), wv.nchunksA, sc);
   return cudaGetLastError();
 }
 

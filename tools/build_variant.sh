@@ -1,0 +1,11 @@
+#!/bin/bash
+# tools/build_variant.sh NAME "-DFLAG=.. -DFLAG2=.."  -> build/variants/NAME.so (kernel tuning experiments)
+set -e
+cd "$(dirname "$0")/../melonix_b200/csrc"
+out=../../build/variants; mkdir -p $out/$1
+for f in capi pv_kernels spec_kernels grain_kernels; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $2 -c $f.cu -o $out/$1/$f.o &
+done
+wait
+nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o $out/$1.so $out/$1/*.o
+echo built $out/$1.so
