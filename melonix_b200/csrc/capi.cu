@@ -56,7 +56,7 @@ struct DevBuf {
 };
 
 struct Tables {
-  DevBuf tw_d, twr_d, tw_f, twr_f, win, win_d, wsyn;
+  DevBuf tw_d, twr_d, tw_f, twr_f, win, win_d, wsyn, decay;
   bool pv_ready = false, spec_ready = false;
 };
 
@@ -159,6 +159,10 @@ int ensure_tables(mlx_ctx* c, int N, bool want_pv, Tables** out) {
     int rc;
     if ((rc = upload_vec(tb.tw_f, twf, c->stream))) return rc;
     if ((rc = upload_vec(tb.twr_f, twrf, c->stream))) return rc;
+    // the reference's window factor expf(-2.5e-4f * (start - i)) (spec.cpp:58), indexed by distance
+    std::vector<float> decay(N + 1);
+    for (int d = 0; d <= N; ++d) decay[d] = expf(-2.5e-4f * (float)d);
+    if ((rc = upload_vec(tb.decay, decay, c->stream))) return rc;
     CK(spec_configure(N));
     tb.spec_ready = true;
   }
@@ -247,10 +251,11 @@ int pv_validate(mlx_ctx* c, const mlx_pv_params* p, PvPlan* pl) {
   const int64_t span = std::max<int64_t>(1, pl->fe - pl->fb);
   // keep at least ~4 CTAs per SM in flight when the job is small
   while (chunk > 16 && (span / chunk) * (int64_t)c->tracks.size() < 4LL * c->sm_count) chunk /= 2;
+  const int GA = pv_group_count_analyze(N);
+  pl->CA = GA * std::max(1, chunk / GA) - 1;  // frames per analysis CTA incl. the halo frame: multiple of GA
   int m = std::max(1, chunk / pl->G);
   while (pl->G * m - 3 < 1) ++m;
-  pl->CA = pl->G * m - 1;
-  pl->CS = pl->G * m - 3;
+  pl->CS = pl->G * m - 3;                     // hops per synthesis CTA (+3 halo frames: multiple of G)
   // wave size.  Default: one wave over the whole range (the intermediates stream through HBM, which
   // has >90 % headroom on this compute-bound path) unless that would take more than a quarter of the
   // device memory; an explicit budget tiles the range so that a wave's intermediates stay in L2.
@@ -454,7 +459,7 @@ void mlx_destroy(mlx_ctx* c) {
     b->release();
   for (auto& kv : c->tables)
     for (DevBuf* b : {&kv.second.tw_d, &kv.second.twr_d, &kv.second.tw_f, &kv.second.twr_f, &kv.second.win,
-                      &kv.second.win_d, &kv.second.wsyn})
+                      &kv.second.win_d, &kv.second.wsyn, &kv.second.decay})
       b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (auto& s : c->slots) {
@@ -569,6 +574,7 @@ static int spec_common(mlx_ctx* c, int track, int fftN, const int* jobs_dev, int
   a.kcol = k;
   a.tw_f = static_cast<const cplx<float>*>(tb->tw_f.p);
   a.twr_f = static_cast<const cplx<float>*>(tb->twr_f.p);
+  a.decay = static_cast<const float*>(tb->decay.p);
   c->mark(3);
   CK(launch_spec(fftN, a, c->stream));
   c->mark(-1);

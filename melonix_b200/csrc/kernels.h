@@ -60,7 +60,8 @@ struct PvScratch {
 };
 
 constexpr int pv_nbp(int fftN) { return fftN / 2 + 32; }
-int pv_group_count(int fftN);        // frames per batch (G)
+int pv_group_count(int fftN);          // frames per batch of the synthesis kernel
+int pv_group_count_analyze(int fftN);  // frames per batch of the analysis kernel
 int pv_threads(int fftN);
 size_t pv_analyze_smem(int fftN);
 size_t pv_synth_smem(int fftN);
@@ -86,6 +87,7 @@ struct SpecArgs {
   float kcol;
   const cplx<float>* tw_f;
   const cplx<float>* twr_f;
+  const float* decay;   // decay[d] = expf(-2.5e-4f * d), d in [0, fftN] (host glibc expf, spec.cpp:58)
 };
 cudaError_t spec_configure(int fftN);
 cudaError_t launch_spec(int fftN, const SpecArgs& a, cudaStream_t st);

@@ -51,16 +51,26 @@ struct PvCfg {
   static constexpr int TILE = N + (G - 1) * H;  // floats per batch tile
   static constexpr int QP = (NC / 2 + THREADS - 1) / THREADS;      // pair slots per thread (k = 1..NC/2)
   static constexpr int QB = (NB + THREADS - 1) / THREADS;          // bin slots per thread
-  static constexpr bool WIN_D = (N <= 4096);                       // double window staged in smem
-  static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUF + (WIN_D ? sizeof(double) * N : 0) +
-                                   sizeof(float) * 2 * TILE + sizeof(float) * 2 * G * NBP + 64;
+  static constexpr bool WIN_D = (N <= 2048);                       // double window staged in smem
+  static constexpr int BUFS = BUF + 1;                             // + one slot for the Nyquist bin's (mag, d)
+  static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUFS + (WIN_D ? sizeof(double) * N : 0) +
+                                   sizeof(float) * 2 * TILE + 64;
   static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + sizeof(float) * 2 * 3 * H + 64;
 };
 
-// G such that G * (N/2) = 4096 complex points per batch -> 256 threads for every N.
+// Frames per batch: synthesis keeps G*(N/2) = 4096 complex points in flight (256 threads, 2 CTAs per
+// SM), analysis 8192 (512 threads, one CTA per SM): 16 resident warps per SM in both kernels.
 template <int N>
 struct PvG {
-  static constexpr int value = 8192 / N;
+  static constexpr int value = 8192 / N;    // K_S
+  static constexpr int analyze = 16384 / N; // K_A
+};
+
+// what the pair phase leaves for the gather phase, stored in the first 8 bytes of the bin's (dead)
+// FFT slot: |X| with the cut-flip flag in its sign bit, and the wrapped phase advance in 2^-32 turns
+struct MagD {
+  float mag;
+  int d;
 };
 
 template <int TPF>
@@ -236,18 +246,18 @@ __global__ void __launch_bounds__(PvCfg<N, G>::THREADS, 1)
 pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = PvCfg<N, G>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NB = Cfg::NB, NBP = Cfg::NBP;
-  constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUF, TILE = Cfg::TILE, QP = Cfg::QP, QB = Cfg::QB;
+  constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUFS, TILE = Cfg::TILE, QP = Cfg::QP, QB = Cfg::QB;
   constexpr bool WD = Cfg::WIN_D;
   using C = cplx<double>;
   using F = Fft<double, NC, -1>;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  C* buf = reinterpret_cast<C*>(smem_raw);                        // [G][BUF]
+  C* buf = reinterpret_cast<C*>(smem_raw);                        // [G][BUF]  Z, then (mag, d) per bin
   double* s_win = reinterpret_cast<double*>(buf + G * BUF);       // [N] when WD
   float* tile = reinterpret_cast<float*>(s_win + (WD ? N : 0));   // [2][TILE]
-  float* s_mag = tile + 2 * TILE;                                 // [G][NBP]
-  int* s_del = reinterpret_cast<int*>(s_mag + G * NBP);           // [G][NBP]  d/(2 pi) * 2^32 (wrapped)
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_del + G * NBP);  // [2]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + 2 * TILE);  // [2]
+  // slot of bin k inside a frame's buffer (bin NC, which has no Z element, uses the extra slot)
+  auto slot = [](int k) { return k == NC ? BUF - 1 : fft_pad(k); };
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
@@ -341,10 +351,8 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
       const long long ff = f_first + gg;
       if (ff >= b) break;
       if (ff < 0) continue;  // frame -1: phi = 0 <=> X = 1 (initial values)
-      const C* zb = buf + gg * BUF;
+      C* zb = buf + gg * BUF;
       const bool emit = (bi != 0 || gg != 0);  // the chunk's leading halo frame only seeds "previous"
-      float* mg = s_mag + gg * NBP;
-      int* dl = s_del + gg * NBP;
 #pragma unroll
       for (int q = 0; q < QP; ++q) {
         const int k = 1 + tid + q * THREADS;
@@ -362,15 +370,10 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           int dq;
           bool flip;
           analysis_bin(xk.x, xk.y, pk[q].x, pk[q].y, ppk[q], pmk[q], k, false, mag, dq, flip);
-          if (emit) {
-            mg[k] = flip ? -mag : mag;  // sign bit of the stored magnitude carries `flip`
-            dl[k] = dq;
-          }
+          // (same thread read these two slots above: overwriting them is race-free)
+          if (emit) *reinterpret_cast<MagD*>(zb + fft_pad(k)) = MagD{flip ? -mag : mag, dq};
           analysis_bin(xm.x, xm.y, pm[q].x, pm[q].y, ppm[q], pmm[q], mbin, false, mag, dq, flip);
-          if (emit) {
-            mg[mbin] = flip ? -mag : mag;
-            dl[mbin] = dq;
-          }
+          if (emit) *reinterpret_cast<MagD*>(zb + fft_pad(mbin)) = MagD{flip ? -mag : mag, dq};
           pk[q] = xk;
           pm[q] = xm;
         }
@@ -382,15 +385,9 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         int dq;
         bool flip;
         analysis_bin(x0, 0.0, p0, 0.0, pp0, pm0, 0, true, mag, dq, flip);
-        if (emit) {
-          mg[0] = flip ? -mag : mag;
-          dl[0] = dq;
-        }
+        if (emit) *reinterpret_cast<MagD*>(zb) = MagD{flip ? -mag : mag, dq};
         analysis_bin(xn, 0.0, pn, 0.0, ppn, pmn, NC, true, mag, dq, flip);
-        if (emit) {
-          mg[NC] = flip ? -mag : mag;
-          dl[NC] = dq;
-        }
+        if (emit) *reinterpret_cast<MagD*>(zb + BUF - 1) = MagD{flip ? -mag : mag, dq};
         p0 = x0;
         pn = xn;
       }
@@ -402,8 +399,8 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     for (int gg = (bi == 0 ? 1 : 0); gg < G; ++gg) {
       const long long ff = f_first + gg;
       if (ff >= b) break;
-      const float* mg = s_mag + gg * NBP;
-      const int* dl = s_del + gg * NBP;
+      const C* zb = buf + gg * BUF;
+      auto magd = [&](int k) { return *reinterpret_cast<const MagD*>(zb + slot(k)); };
       const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
       float r = wv.rate;
       uint32_t r_fix = (uint32_t)wv.r_fix;  // rate * 2^26 <= 2^28
@@ -425,14 +422,15 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
           const bool any = klo <= khi;       // K_j non-empty (at most one bin when rate >= 1)
           const int kh = any ? khi : 0;
-          float smag = any ? fabsf(mg[klo]) : 0.f;
-          for (int k = klo + 1; k <= khi; ++k) smag += fabsf(mg[k]);  // only when rate < 1
+          const MagD mh = magd(kh);  // the bin whose frequency the output bin inherits
+          float smag = any ? fabsf(klo == khi ? mh.mag : magd(klo).mag) : 0.f;
+          for (int k = klo + 1; k <= khi; ++k) smag += fabsf(magd(k).mag);  // only when rate < 1
           // frac(rate * nu / 4) * 2^32 with nu / 4 = (khi * 2^30 + d) / 2^32 turns, d the signed phase
           // advance (+-2^32 when the cut decision says so): one exact product mod 2^64, rounded once
           // -- the same single rounding per frame as the oracle's llrint.  32-bit pieces:
-          const int d32 = dl[kh];
+          const int d32 = mh.d;
           int dhi = d32 >> 31;
-          dhi += (__float_as_uint(mg[kh]) >> 31) ? ((d32 < 0) ? 1 : -1) : 0;
+          dhi += (__float_as_uint(mh.mag) >> 31) ? ((d32 < 0) ? 1 : -1) : 0;
           const uint32_t k30 = (uint32_t)kh << 30;
           const uint32_t nlo = k30 + (uint32_t)d32;
           const uint32_t nhi = (uint32_t)(kh >> 2) + (uint32_t)dhi + (nlo < k30 ? 1u : 0u);
@@ -453,11 +451,11 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
       for (int gg = warp + (bi == 0 ? 1 : 0); gg < G; gg += THREADS / 32) {
         const long long ff = f_first + gg;
         if (ff >= b || ff >= wv.we) break;
-        const float* mg = s_mag + gg * NBP;
+        const C* zb = buf + gg * BUF;
         float best = -1.f;
         int bk = wv.kmin;
         for (int k = wv.kmin + lane; k <= wv.kmax; k += 32) {
-          const float v = fabsf(mg[k]);
+          const float v = fabsf(reinterpret_cast<const MagD*>(zb + slot(k))->mag);
           if (v > best) { best = v; bk = k; }
         }
 #pragma unroll
@@ -469,8 +467,9 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         if (lane == 0) {
           if (tr.peak) tr.peak[ff] = bk;
           if (tr.f0) {
-            long long dd = (long long)s_del[gg * NBP + bk];
-            if (__float_as_uint(mg[bk]) >> 31) dd += (dd < 0) ? 4294967296LL : -4294967296LL;
+            const MagD mb = *reinterpret_cast<const MagD*>(zb + slot(bk));
+            long long dd = (long long)mb.d;
+            if (__float_as_uint(mb.mag) >> 31) dd += (dd < 0) ? 4294967296LL : -4294967296LL;
             tr.f0[ff] = ((float)bk + (float)dd * 9.313225746154785e-10f) * wv.fs_over_N;  // nu = k + 4 d
           }
         }
@@ -733,9 +732,9 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
 // ------------------------------------------------------------------------------------------------
 template <int N>
 static cudaError_t configure_n() {
-  constexpr int G = PvG<N>::value;
-  cudaError_t e = cudaFuncSetAttribute(pv_analyze_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)PvCfg<N, G>::SMEM_A);
+  constexpr int G = PvG<N>::value, GA = PvG<N>::analyze;
+  cudaError_t e = cudaFuncSetAttribute(pv_analyze_kernel<N, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)PvCfg<N, GA>::SMEM_A);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(pv_synth_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)PvCfg<N, G>::SMEM_S);
@@ -756,14 +755,15 @@ cudaError_t pv_configure(int fftN) {
   return cudaSuccess;
 }
 int pv_group_count(int fftN) { return 8192 / fftN; }
+int pv_group_count_analyze(int fftN) { return 16384 / fftN; }
 int pv_threads(int) { return 256; }
 size_t pv_analyze_smem(int fftN) {
   switch (fftN) {
-    case 512: return PvCfg<512, 16>::SMEM_A;
-    case 1024: return PvCfg<1024, 8>::SMEM_A;
-    case 2048: return PvCfg<2048, 4>::SMEM_A;
-    case 4096: return PvCfg<4096, 2>::SMEM_A;
-    case 8192: return PvCfg<8192, 1>::SMEM_A;
+    case 512: return PvCfg<512, 32>::SMEM_A;
+    case 1024: return PvCfg<1024, 16>::SMEM_A;
+    case 2048: return PvCfg<2048, 8>::SMEM_A;
+    case 4096: return PvCfg<4096, 4>::SMEM_A;
+    case 8192: return PvCfg<8192, 2>::SMEM_A;
   }
   return 0;
 }
@@ -781,7 +781,7 @@ size_t pv_synth_smem(int fftN) {
 cudaError_t launch_pv_analyze(int fftN, const PvTrack* tracks, int ntracks, const PvWave& wv,
                               const PvTables& tb, const PvScratch& sc, cudaStream_t st) {
   MLX_PV_DISPATCH(fftN, {
-    constexpr int G = PvG<N>::value;
+    constexpr int G = PvG<N>::analyze;
     dim3 grid(wv.nchunksA, ntracks);
     pv_analyze_kernel<N, G><<<grid, PvCfg<N, G>::THREADS, PvCfg<N, G>::SMEM_A, st>>>(tracks, wv, tb, sc);
   });

@@ -21,7 +21,8 @@ struct SpecCfg {
   static constexpr int JPB = TPF >= 256 ? 1 : 256 / TPF;  // jobs in flight per CTA
   static constexpr int THREADS = JPB * TPF;
   static constexpr int BUF = FftPlan<NC>::BUF;
-  static constexpr size_t SMEM = sizeof(cplx<float>) * JPB * BUF;
+  static constexpr bool TAB = (N <= 8192);  // window-factor table staged in shared memory
+  static constexpr size_t SMEM = sizeof(cplx<float>) * JPB * BUF + (TAB ? sizeof(float) * (N + 4) : 0);
 };
 
 template <int TPF>
@@ -38,6 +39,13 @@ struct SpecBar {
     }
   }
 };
+
+// sqrt.approx: ~1 ulp, far inside the 1e-4 RMS budget of the float magnitudes
+__device__ __forceinline__ float spec_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // colour ramp, reference spec-cache.cpp:79-96 (note 255/3 == 85 and 2*255/3 == 170: int division)
 __device__ __forceinline__ void colour_ramp(float v, float k, unsigned char* rgb) {
@@ -64,18 +72,28 @@ __device__ __forceinline__ void colour_ramp(float v, float k, unsigned char* rgb
   rgb[2] = b;
 }
 
+#ifndef MLX_SPEC_MINB
+#define MLX_SPEC_MINB 3
+#endif
+
 template <int N>
-__global__ void __launch_bounds__(SpecCfg<N>::THREADS) spec_kernel(const SpecArgs a) {
+__global__ void __launch_bounds__(SpecCfg<N>::THREADS, SpecCfg<N>::THREADS >= 512 ? 1 : MLX_SPEC_MINB)
+spec_kernel(const SpecArgs a) {
   using Cfg = SpecCfg<N>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, JPB = Cfg::JPB, BUF = Cfg::BUF;
   using C = cplx<float>;
   using F = Fft<float, NC, -1>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* bufs = reinterpret_cast<C*>(smem_raw);
+  float* s_decay = reinterpret_cast<float*>(bufs + JPB * BUF);  // [N + 1] when Cfg::TAB
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
   C* buf = bufs + g * BUF;
+  if constexpr (Cfg::TAB) {
+    for (int d = tid; d <= N; d += Cfg::THREADS) s_decay[d] = a.decay[d];
+    __syncthreads();
+  }
   FftTwiddles<float, NC, -1> twd;
   twd.init(t, a.tw_f);
   unsigned mask = 0xffffffffu;
@@ -93,17 +111,27 @@ __global__ void __launch_bounds__(SpecCfg<N>::THREADS) spec_kernel(const SpecArg
       end = start + a.hop;
     }
     C x[16];
+    // window [end-N, end): zero outside [0, n); samples before `start` are multiplied by
+    // expf(-2.5e-4f * (start - i)) -- a float product, as spec.cpp:58.  The factor depends only on
+    // the integer distance start - i <= N; for N <= 8192 it comes from a shared-memory copy of a
+    // table the host filled with glibc's expf (the reference's own arithmetic).
+    const long long base = end - N;
+    const bool interior = base >= 0 && end <= a.n;  // whole window inside the track: no bounds tests
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-      const long long i0 = end - N + 2 * (t + m * TPF);
+      const int p = 2 * (t + m * TPF);  // position inside the window
       float v[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const long long i = i0 + c;
+        const long long i = base + p + c;
         float s = 0.f;
-        if (i >= 0 && i < a.n) {
-          s = a.x[i];
-          if (i < start) s = __fmul_rn(expf(-2.5e-4f * (float)(int)(start - i)), s);
+        if (interior || (i >= 0 && i < a.n)) s = __ldg(a.x + i);
+        const long long dist = start - i;  // > 0: before `start`
+        if (dist > 0) {
+          float w;
+          if (Cfg::TAB && dist <= N) w = s_decay[dist];
+          else w = expf(-2.5e-4f * (float)(int)dist);
+          s = __fmul_rn(w, s);
         }
         v[c] = s;
       }
@@ -132,8 +160,8 @@ __global__ void __launch_bounds__(SpecCfg<N>::THREADS) spec_kernel(const SpecArg
         const float tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
         const float xkr = er + ti_, xki = ei - tr_;
         const float xmr = er - ti_, xmi = -ei - tr_;
-        mk = sqrtf(xkr * xkr + xki * xki);
-        mm = sqrtf(xmr * xmr + xmi * xmi);
+        mk = spec_sqrt(fmaf(xkr, xkr, xki * xki));
+        mm = spec_sqrt(fmaf(xmr, xmr, xmi * xmi));
       }
       mk *= inv_n;
       mm *= inv_n;
