@@ -50,7 +50,7 @@ struct PvCfg {
   static constexpr int BUF = FftPlan<NC>::BUF;
   static constexpr int TILE = N + (G - 1) * H;  // floats per batch tile
   static constexpr int QP = (NC / 2 + THREADS - 1) / THREADS;      // pair slots per thread (k = 1..NC/2)
-  static constexpr int QB = (NB + THREADS - 1) / THREADS;          // bin slots per thread
+  static constexpr int QB = (NC + THREADS - 1) / THREADS;          // bin slots per thread (bins 0..NC-1; bin NC: last warp)
   static constexpr bool WIN_D = (N <= 2048);                       // double window staged in smem
   static constexpr int BUFS = BUF + 1;                             // + one slot for the Nyquist bin's (mag, d)
   static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUFS + (WIN_D ? sizeof(double) * N : 0) +
@@ -180,19 +180,36 @@ __device__ __forceinline__ void analysis_bin(double a, double b, double c, doubl
   uint32_t P = __float2uint_rn(pabs * 683565275.5764316f);  // 2^32 / (2 pi); pabs <= pi -> <= 2^31
   P = (__float_as_uint(bf) >> 31) ? (0u - P) : P;
   d32 = (int)(P - p_prev - ((uint32_t)bin << 30));
-  // the double component that ends up as Im Z: odd bins -> -(ac + bd), even bins -> (bc - ad)
-  const bool odd = bin & 1, neg = bin & 2;
-  const double u = odd ? a : b, v = odd ? b : -a;
-  const double s64 = fma(u, c, v * d);
-  unsigned sbit = ((unsigned)__double2hiint(s64) >> 31) ^ (odd ? 1u : 0u) ^ (neg ? 1u : 0u);
-  if (real_bin) sbit = 0u;  // bins 0 and N/2 are purely real: Im Z := +0, d in {0, +pi}
   const bool gate = mag * mag_prev <= 1e-18f;  // silence gate |Z| <= 1e-18 -> d = 0
   const unsigned dneg = (unsigned)d32 >> 31;
   const unsigned dabs = dneg ? (0u - (unsigned)d32) : (unsigned)d32;
-  flip = !gate && dabs > 0x40000000u && dneg != sbit;
+  flip = false;
+  // Only within 2^20 counts (1.5e-3 rad) of the +-pi cut can the float phases put d on the wrong
+  // side (their error is ~1e-7 rad); only there the DOUBLE product decides.  Component of
+  // X conj(Xprev) (-i)^bin that ends up as Im Z: odd bins -> -(ac + bd), even bins -> (bc - ad).
+  if (!gate && dabs > 0x7FF00000u) {
+    const bool odd = bin & 1, neg = bin & 2;
+    const double u = odd ? a : b, v = odd ? b : -a;
+    const double s64 = fma(u, c, v * d);
+    unsigned sbit = ((unsigned)__double2hiint(s64) >> 31) ^ (odd ? 1u : 0u) ^ (neg ? 1u : 0u);
+    if (real_bin) sbit = 0u;  // bins 0 and N/2 are purely real: Im Z := +0, d in {0, +pi}
+    flip = dneg != sbit;
+  }
   d32 = gate ? 0 : d32;
   p_prev = P;
   mag_prev = mag;
+}
+
+// The purely real bins 0 and N/2: arg X is 0 or pi, Im Z := +0 (PV-spec v1), so d is 0 or +pi.
+// Same result as analysis_bin(real_bin = true) at a fraction of its cost.
+__device__ __forceinline__ MagD analysis_real_bin(double x, uint32_t& p_prev, float& mag_prev) {
+  const float mag = fabsf((float)x);
+  const uint32_t P = x < 0.0 ? 0x80000000u : 0u;
+  const bool gate = mag * mag_prev <= 1e-18f;
+  const bool turned = (P != p_prev) && !gate;  // d = +pi: stored as -2^31 with the flip flag set
+  p_prev = P;
+  mag_prev = mag;
+  return MagD{turned ? -mag : mag, turned ? (int)0x80000000u : 0};
 }
 
 // trunc(float(k) * r) with a plain float multiply, exactly as the spec (A.5) and the oracle do.
@@ -212,6 +229,33 @@ __device__ __noinline__ void gather_entry_slow(int j, float r, int NC, uint32_t&
   int khi = k;
   while (khi + 1 <= NC && shift_bin(khi + 1, r) == j) ++khi;
   kk = (uint32_t)k | ((uint32_t)khi << 16);
+}
+
+// Bin shift + exact phase increment of one output bin j for one frame (PV-spec A.5/A.6).
+// `zb` holds the frame's (mag, d) records.  Returns the shifted magnitude; inc = uint32 increment.
+template <int NC, int BUF>
+__device__ __forceinline__ float shift_one_bin(const cplx<double>* zb, int j, uint32_t kk, uint32_t r_fix,
+                                               uint32_t& inc) {
+  auto magd = [&](int k) { return *reinterpret_cast<const MagD*>(zb + (k == NC ? BUF - 1 : fft_pad(k))); };
+  const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
+  const bool any = klo <= khi;  // K_j non-empty (at most one bin when rate >= 1)
+  const int kh = any ? khi : 0;
+  const MagD mh = magd(kh);  // the bin whose frequency the output bin inherits
+  float smag = any ? fabsf(klo == khi ? mh.mag : magd(klo).mag) : 0.f;
+  for (int k = klo + 1; k <= khi; ++k) smag += fabsf(magd(k).mag);  // only when rate < 1
+  // frac(rate * nu / 4) * 2^32 with nu / 4 = (khi * 2^30 + d) / 2^32 turns, d the signed phase advance
+  // (+-2^32 when the cut decision says so): one exact product mod 2^64, rounded once -- the same
+  // single rounding per frame as the oracle's llrint.  32-bit pieces:
+  const int d32 = mh.d;
+  int dhi = d32 >> 31;
+  dhi += (__float_as_uint(mh.mag) >> 31) ? ((d32 < 0) ? 1 : -1) : 0;
+  const uint32_t k30 = (uint32_t)kh << 30;
+  const uint32_t nlo = k30 + (uint32_t)d32;
+  const uint32_t nhi = (uint32_t)(kh >> 2) + (uint32_t)dhi + (nlo < k30 ? 1u : 0u);
+  const unsigned long long prod =
+      (unsigned long long)r_fix * nlo + ((unsigned long long)(r_fix * nhi) << 32) + (1ULL << 25);
+  inc = any ? (uint32_t)(prod >> 26) : (((uint32_t)j & 3u) << 30);  // empty K_j: s_nu = j -> frac(j / 4)
+  return smag;
 }
 
 // sin/cos of 2*pi*acc/2^32: the quadrant comes from the top bits (exact range reduction for free),
@@ -302,12 +346,12 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     ppk[q] = ppm[q] = 0u;
     pmk[q] = pmm[q] = 1.f;
   }
-  double p0 = 1.0, pn = 1.0;  // previous X[0], X[NC] (real)
   uint32_t pp0 = 0u, ppn = 0u;
   float pm0 = 1.f, pmn = 1.f;
   uint32_t lacc[QB], totc[QB];  // chunk-local phase sum; its value at the last frame < we
 #pragma unroll
   for (int q = 0; q < QB; ++q) lacc[q] = totc[q] = 0u;
+  uint32_t lacc_nyq = 0u, totc_nyq = 0u;  // bin NC, kept by every lane of the last warp
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
   const size_t row0 = (size_t)blockIdx.y * wv.rows;
   const bool per_frame_rate = tr.rate_pf != nullptr;
@@ -378,18 +422,14 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           pm[q] = xm;
         }
       }
-      if (tid == 0) {  // DC and Nyquist are real: X[0] = Re Z0 + Im Z0, X[NC] = Re Z0 - Im Z0
+      if (tid == THREADS - 1) {  // DC and Nyquist are real: X[0] = Re Z0 + Im Z0, X[NC] = Re Z0 - Im Z0
         const C z0 = zb[0];
-        const double x0 = z0.x + z0.y, xn = z0.x - z0.y;
-        float mag;
-        int dq;
-        bool flip;
-        analysis_bin(x0, 0.0, p0, 0.0, pp0, pm0, 0, true, mag, dq, flip);
-        if (emit) *reinterpret_cast<MagD*>(zb) = MagD{flip ? -mag : mag, dq};
-        analysis_bin(xn, 0.0, pn, 0.0, ppn, pmn, NC, true, mag, dq, flip);
-        if (emit) *reinterpret_cast<MagD*>(zb + BUF - 1) = MagD{flip ? -mag : mag, dq};
-        p0 = x0;
-        pn = xn;
+        const MagD m0 = analysis_real_bin(z0.x + z0.y, pp0, pm0);
+        const MagD mn = analysis_real_bin(z0.x - z0.y, ppn, pmn);
+        if (emit) {
+          *reinterpret_cast<MagD*>(zb) = m0;
+          *reinterpret_cast<MagD*>(zb + BUF - 1) = mn;
+        }
       }
     }
     __syncthreads();
@@ -400,7 +440,6 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
       const long long ff = f_first + gg;
       if (ff >= b) break;
       const C* zb = buf + gg * BUF;
-      auto magd = [&](int k) { return *reinterpret_cast<const MagD*>(zb + slot(k)); };
       const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
       float r = wv.rate;
       uint32_t r_fix = (uint32_t)wv.r_fix;  // rate * 2^26 <= 2^28
@@ -412,36 +451,60 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
         const int j = tid + q * THREADS;
-        if (j < NB) {
-          uint32_t kk;
+        if (j < NC) {
+          uint32_t kk, inc;
           if (per_frame_rate) {
             gather_entry_slow(j, r, NC, kk);
           } else {
             kk = __ldg(wv.gk + j);
           }
-          const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
-          const bool any = klo <= khi;       // K_j non-empty (at most one bin when rate >= 1)
-          const int kh = any ? khi : 0;
-          const MagD mh = magd(kh);  // the bin whose frequency the output bin inherits
-          float smag = any ? fabsf(klo == khi ? mh.mag : magd(klo).mag) : 0.f;
-          for (int k = klo + 1; k <= khi; ++k) smag += fabsf(magd(k).mag);  // only when rate < 1
-          // frac(rate * nu / 4) * 2^32 with nu / 4 = (khi * 2^30 + d) / 2^32 turns, d the signed phase
-          // advance (+-2^32 when the cut decision says so): one exact product mod 2^64, rounded once
-          // -- the same single rounding per frame as the oracle's llrint.  32-bit pieces:
-          const int d32 = mh.d;
-          int dhi = d32 >> 31;
-          dhi += (__float_as_uint(mh.mag) >> 31) ? ((d32 < 0) ? 1 : -1) : 0;
-          const uint32_t k30 = (uint32_t)kh << 30;
-          const uint32_t nlo = k30 + (uint32_t)d32;
-          const uint32_t nhi = (uint32_t)(kh >> 2) + (uint32_t)dhi + (nlo < k30 ? 1u : 0u);
-          const unsigned long long prod =
-              (unsigned long long)r_fix * nlo + ((unsigned long long)(r_fix * nhi) << 32) + (1ULL << 25);
-          const uint32_t inc = any ? (uint32_t)(prod >> 26) : (((uint32_t)j & 3u) << 30);
+          const float smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
           lacc[q] += inc;
           if (counted) totc[q] = lacc[q];
           sc.smag[row + j] = smag;
           sc.lacc[row + j] = lacc[q];
         }
+      }
+    }
+
+    // ---- the Nyquist output bin j = NC does not fit the bins-per-thread tiling: the last warp takes
+    //      it for the whole batch, one lane per frame, with a warp scan for the running phase
+    if (tid >= THREADS - 32) {
+      const int lane = tid & 31;
+      for (int g0 = 0; g0 < G; g0 += 32) {
+        const int gg = g0 + lane;
+        const long long ff = f_first + gg;
+        const bool valid = gg < G && gg >= (bi == 0 ? 1 : 0) && ff < b;
+        uint32_t inc = 0u;
+        float smag = 0.f;
+        if (valid) {
+          float r = wv.rate;
+          uint32_t r_fix = (uint32_t)wv.r_fix, kk;
+          if (per_frame_rate) {
+            r = tr.rate_pf[ff];
+            r_fix = (uint32_t)((double)r * 67108864.0);
+            gather_entry_slow(NC, r, NC, kk);
+          } else {
+            kk = __ldg(wv.gk + NC);
+          }
+          smag = shift_one_bin<NC, BUF>(buf + gg * BUF, NC, kk, r_fix, inc);
+        }
+        uint32_t run = inc;  // inclusive scan over the lanes (= frames, ascending)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, run, o);
+          if (lane >= o) run += v;
+        }
+        const uint32_t mine = lacc_nyq + run;
+        if (valid) {
+          const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
+          sc.smag[row + NC] = smag;
+          sc.lacc[row + NC] = mine;
+        }
+        // phase at the last frame before the wave end (carried into the next wave)
+        const unsigned cm = __ballot_sync(0xffffffffu, valid && ff < wv.we);
+        if (cm) totc_nyq = __shfl_sync(0xffffffffu, mine, 31 - __clz(cm));
+        lacc_nyq += __shfl_sync(0xffffffffu, run, 31);
       }
     }
 
@@ -481,10 +544,14 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 #pragma unroll
   for (int q = 0; q < QB; ++q) {
     const int j = tid + q * THREADS;
-    if (j < NB) {
+    if (j < NC) {
       sc.tot[trow + j] = lacc[q];    // all frames of the chunk: prefix of the later chunks of this wave
       sc.totc[trow + j] = totc[q];   // frames < we only: what the next wave starts from
     }
+  }
+  if (tid == THREADS - 1) {
+    sc.tot[trow + NC] = lacc_nyq;
+    sc.totc[trow + NC] = totc_nyq;
   }
 }
 

@@ -109,6 +109,28 @@ def test_no_drift_on_stationary_tones(engine, oracle):
     assert np.array_equal(g["peak"], o["peak"])
 
 
+def test_cut_decision_on_noise(engine, oracle):
+    """White noise puts every bin's phase advance uniformly on the circle: hundreds of full-scale
+    bin-frames fall within 1.5e-3 rad of the +-pi cut, where K_A takes the sign from the DOUBLE product
+    X conj(Xprev) (-i)^k.  A wrong sign there offsets that bin's phase by frac(rate) turns for the
+    rest of the track, so the RMS bound checks the cut logic on all of them."""
+    N, H = 2048, 512
+    n = 48000 * 6
+    x = (0.1 * np.random.default_rng(2024).standard_normal(n)).astype(np.float32)
+    F = (n + H - 1) // H
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32).astype(np.float64)
+    xp = np.concatenate([np.zeros(N), x.astype(np.float64), np.zeros(N)])
+    X = np.stack([np.fft.rfft(xp[(f + 1) * H:(f + 1) * H + N] * w) for f in range(F)])
+    Z = X[1:] * np.conj(X[:-1]) * ((-1j) ** np.arange(N // 2 + 1))
+    near = (np.abs(np.abs(np.angle(Z)) - np.pi) < 1.5e-3) & (np.abs(Z) > 1.0)
+    assert near.sum() >= 100
+    engine.upload_tracks([x])
+    for semis in (3.0, -7.0):
+        g = engine.pv_run(N, H, ratio(semis))[0]
+        o = oracle.pv_run(x, N, H, ratio(semis))
+        assert rms(g["y"], o["y"]) <= 1e-4 and rms(g["y"], o["y"]) < 1e-6
+
+
 def test_wave_tiling_and_chunking_are_bitwise_invisible(engine, monkeypatch):
     xs = [S.vibrato_tone(6.0, seed=21), S.vibrato_tone(4.3, seed=22)]
     engine.upload_tracks(xs)
