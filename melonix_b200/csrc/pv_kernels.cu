@@ -236,7 +236,8 @@ __device__ __noinline__ void gather_entry_slow(int j, float r, int NC, uint32_t&
 template <int NC, int BUF>
 __device__ __forceinline__ float shift_one_bin(const cplx<double>* zb, int j, uint32_t kk, uint32_t r_fix,
                                                uint32_t& inc) {
-  auto magd = [&](int k) { return *reinterpret_cast<const MagD*>(zb + (k == NC ? BUF - 1 : fft_pad(k))); };
+  // fft_pad(NC) == BUF - 1: the extra slot of the Nyquist bin is where the padding formula puts it
+  auto magd = [&](int k) { return *reinterpret_cast<const MagD*>(zb + fft_pad(k)); };
   const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
   const bool any = klo <= khi;  // K_j non-empty (at most one bin when rate >= 1)
   const int kh = any ? khi : 0;
@@ -300,8 +301,8 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   double* s_win = reinterpret_cast<double*>(buf + G * BUF);       // [N] when WD
   float* tile = reinterpret_cast<float*>(s_win + (WD ? N : 0));   // [2][TILE]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + 2 * TILE);  // [2]
-  // slot of bin k inside a frame's buffer (bin NC, which has no Z element, uses the extra slot)
-  auto slot = [](int k) { return k == NC ? BUF - 1 : fft_pad(k); };
+  static_assert(fft_pad(NC) == BUF - 1, "the Nyquist bin's (mag, d) record uses the extra slot");
+  auto slot = [](int k) { return fft_pad(k); };
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
@@ -335,6 +336,12 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   FftTwiddles<double, NC, -1> twd;
   twd.init(t, tb.tw_d);
   // pair slots: bins k and NC-k for k = 1 + tid + q*THREADS <= NC/2; thread 0 also owns (0, NC)
+  C wpair[QP];  // exp(-2 pi i k / N) of this thread's pairs
+#pragma unroll
+  for (int q = 0; q < QP; ++q) {
+    const int k = 1 + tid + q * THREADS;
+    wpair[q] = tb.twr_d[k <= NC / 2 ? k : 0];
+  }
   // previous frame per bin: X (double, for the cut decision), integer phase, magnitude.
   // Frame -1 has phi = 0 <=> X = 1.
   C pk[QP], pm[QP];
@@ -352,9 +359,17 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 #pragma unroll
   for (int q = 0; q < QB; ++q) lacc[q] = totc[q] = 0u;
   uint32_t lacc_nyq = 0u, totc_nyq = 0u;  // bin NC, kept by every lane of the last warp
+  const bool per_frame_rate = tr.rate_pf != nullptr;
+  // constant-rate path: the bin-shift table entries of this thread's bins are frame-invariant
+  uint32_t gkq[QB];
+#pragma unroll
+  for (int q = 0; q < QB; ++q) {
+    const int j = tid + q * THREADS;
+    gkq[q] = (!per_frame_rate && j < NC) ? __ldg(wv.gk + j) : 1u;
+  }
+  const uint32_t gk_nyq = per_frame_rate ? 1u : __ldg(wv.gk + NC);
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
   const size_t row0 = (size_t)blockIdx.y * wv.rows;
-  const bool per_frame_rate = tr.rate_pf != nullptr;
 
   for (int bi = 0; bi < nbatch; ++bi) {
     const long long f_first = a - 1 + (long long)bi * G;
@@ -404,7 +419,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           const int mbin = NC - k;
           const C za = zb[fft_pad(k)];
           const C zc = zb[fft_pad(mbin)];
-          const C w = tb.twr_d[k];
+          const C w = wpair[q];
           const double er = 0.5 * (za.x + zc.x), ei = 0.5 * (za.y - zc.y);
           const double dr = 0.5 * (za.x - zc.x), di = 0.5 * (za.y + zc.y);
           const double tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
@@ -456,7 +471,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           if (per_frame_rate) {
             gather_entry_slow(j, r, NC, kk);
           } else {
-            kk = __ldg(wv.gk + j);
+            kk = gkq[q];
           }
           const float smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
           lacc[q] += inc;
@@ -485,7 +500,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
             r_fix = (uint32_t)((double)r * 67108864.0);
             gather_entry_slow(NC, r, NC, kk);
           } else {
-            kk = __ldg(wv.gk + NC);
+            kk = gk_nyq;
           }
           smag = shift_one_bin<NC, BUF>(buf + gg * BUF, NC, kk, r_fix, inc);
         }

@@ -137,31 +137,39 @@ def exclusive_phase_prefix(totals: torch.Tensor, world: int, rank: int, group=No
     return acc
 
 
-def run_time_sharded(engine, own: torch.Tensor, n_total: int, fft_n: int, hop: int, rate: float,
+def run_time_sharded(engine, owns, n_total: int, fft_n: int, hop: int, rate: float,
                      sample_rate: float = 48000.0, group=None):
-    """Phase-vocodes ONE long mono track sharded by time range across the ranks of `group`.
+    """Phase-vocodes long mono track(s) of n_total samples sharded by time range across the ranks of
+    `group` (BASELINE configs[3]: "stereo" = two planar mono tracks).
 
-    own: this rank's owned samples (CUDA float32, global samples [own_lo, own_hi) of
-    plan_time_shards(...)[rank]).  Returns (y_own, peak_own, f0_own): the owned output samples and the
-    owned frames' peak bins / f0, all on the device.  Bit-identical to the unsharded run."""
+    owns: this rank's owned samples, one CUDA float32 tensor per track (global samples
+    [own_lo, own_hi) of plan_time_shards(...)[rank]); a single tensor is accepted too.
+    Returns per track (y_own, peak_own, f0_own): the owned output samples and the owned frames' peak
+    bins / f0, on the device.  Bit-identical to the unsharded run."""
+    single = isinstance(owns, torch.Tensor)
+    owns = [owns] if single else list(owns)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     shard = plan_time_shards(n_total, fft_n, hop, world)[rank]
-    window = exchange_seam_samples(own, shard, world, group)          # seam exchange (1)
+    windows = [exchange_seam_samples(o, shard, world, group) for o in owns]     # seam exchange (1)
+    dev = owns[0].device
     engine.use_torch_stream()
-    engine.upload_tracks_dev([window])
+    engine.upload_tracks_dev(windows)
     nb = fft_n // 2 + 1
+    nt = len(owns)
     lb, le = shard.local_frame_begin, shard.local_frame_end
-    totals32 = torch.zeros(nb, dtype=torch.int32, device=own.device)
-    F_local = num_frames(window.numel(), hop)
-    peak = torch.zeros(F_local, dtype=torch.int32, device=own.device)
-    f0 = torch.zeros(F_local, dtype=torch.float32, device=own.device)
-    engine.pv_phase_totals_dev(fft_n, hop, rate, [totals32], sample_rate=sample_rate, frame_begin=lb,
-                               frame_end=le, wave_mib=-1)
-    totals = (totals32.to(torch.int64) & 0xFFFFFFFF).unsqueeze(0)
-    carry = exclusive_phase_prefix(totals, world, rank, group)[0]   # phase carry (2)
-    carry32 = torch.where(carry >= 2 ** 31, carry - 2 ** 32, carry).to(torch.int32)
-    y = torch.zeros_like(window)
-    engine.pv_run_dev(fft_n, hop, rate, [y], [peak], [f0], sample_rate=sample_rate, frame_begin=lb,
-                      frame_end=le, phase_in=[carry32], wave_mib=-1)
+    F_local = num_frames(windows[0].numel(), hop)
+    totals32 = torch.zeros((nt, nb), dtype=torch.int32, device=dev)
+    peak = torch.zeros((nt, F_local), dtype=torch.int32, device=dev)
+    f0 = torch.zeros((nt, F_local), dtype=torch.float32, device=dev)
+    engine.pv_phase_totals_dev(fft_n, hop, rate, [totals32[t] for t in range(nt)], sample_rate=sample_rate,
+                               frame_begin=lb, frame_end=le, wave_mib=-1)
+    totals = totals32.to(torch.int64) & 0xFFFFFFFF
+    carry = exclusive_phase_prefix(totals, world, rank, group)                  # phase carry (2)
+    carry32 = torch.where(carry >= 2 ** 31, carry - 2 ** 32, carry).to(torch.int32).contiguous()
+    ys = [torch.zeros_like(w) for w in windows]
+    engine.pv_run_dev(fft_n, hop, rate, ys, [peak[t] for t in range(nt)], [f0[t] for t in range(nt)],
+                      sample_rate=sample_rate, frame_begin=lb, frame_end=le,
+                      phase_in=[carry32[t] for t in range(nt)], wave_mib=-1)
     lo = shard.left_halo
-    return y[lo:lo + own.numel()], peak[lb:le], f0[lb:le]
+    out = [(ys[t][lo:lo + owns[t].numel()], peak[t, lb:le], f0[t, lb:le]) for t in range(nt)]
+    return out[0] if single else out
