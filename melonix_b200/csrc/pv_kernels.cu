@@ -55,7 +55,7 @@ struct PvCfg {
   static constexpr int BUFS = BUF + 1;                             // + one slot for the Nyquist bin's (mag, d)
   static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUFS + (WIN_D ? sizeof(double) * N : 0) +
                                    sizeof(float) * 2 * TILE + 64;
-  static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + sizeof(float) * 2 * 3 * H + 64;
+  static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + 64;
 };
 
 // Frames per batch: synthesis keeps G*(N/2) = 4096 complex points in flight (256 threads, 2 CTAs per
@@ -623,13 +623,13 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NBP = Cfg::NBP;
   constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUF, QP = Cfg::QP;
   constexpr int H2 = H / 2;
+  constexpr int COLS = (H2 + THREADS - 1) / THREADS;  // overlap-add columns (float2) per thread
   constexpr int GS = G < 4 ? G : 4;  // frames whose loads are in flight together
   using C = cplx<float>;
   using F = Fft<float, NC, +1>;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  C* buf = reinterpret_cast<C*>(smem_raw);                   // [G][BUF]
-  float2* carry = reinterpret_cast<float2*>(buf + G * BUF);  // [2][3][H/2]
+  C* buf = reinterpret_cast<C*>(smem_raw);  // [G][BUF]
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
@@ -667,7 +667,20 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   const size_t row0 = (size_t)blockIdx.y * wv.rows + (size_t)(a - wv.wb);
   const int a_off = (int)(a - wv.wb);
   int next_chunk_at = 0;  // frame (relative to a) at which the analysis chunk, hence the prefix, changes
-  int cb = 0;             // carry buffer holding partial sums of the three pending hops
+  float2 p0[COLS], p1[COLS], p2[COLS];  // pending overlap-add sums of the three youngest hops
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) p0[c] = p1[c] = p2[c] = make_float2(0.f, 0.f);
+  // hop `hrel` (relative to a) of column i2: written only if this chunk owns it
+  auto emit_hop = [&](int hrel, int i2, float2 v) {
+    if (hrel >= 0 && hrel < nhop) {
+      const long long o = (a + hrel) * H + 2 * i2;
+      if (o + 1 < tr.n) {
+        *reinterpret_cast<float2*>(tr.out + o) = v;
+      } else if (o < tr.n) {
+        tr.out[o] = v.x;
+      }
+    }
+  };
 
   for (int bi = 0; bi < nbatch; ++bi) {
     const int fb = bi * G;                       // frame index relative to a
@@ -768,46 +781,42 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     }
     __syncthreads();
 
-    // ---- overlap-add.  Hop h = samples [hH, (h+1)H) = sum over frames f = h..h+3 of
-    //      y_f[(h-f+3)H + i], added in ascending f.  This batch completes hops fb-3 .. fb+G-4 and
-    //      leaves partial sums of the last three in the other carry buffer.
-    {
-      const float2* cin = carry + cb * 3 * H2;
-      float2* cout = carry + (cb ^ 1) * 3 * H2;
-      const int h_min = -min(3, fb);  // hops before the chunk's first (fb + hr < 0) belong to the previous CTA
-      const int last_g = nfr - 1;
-      const int last_needed_cap = nfr_total - 1 - fb;  // index (relative to fb) of the chunk's last frame
-#pragma unroll 1
-      for (int it = tid; it < (G + 3) * H2; it += THREADS) {
-        const int hh = it / H2, i2 = it % H2;
-        const int hr = hh - 3;  // hop relative to fb
-        if (hr < h_min) continue;
-        float2 s = make_float2(0.f, 0.f);
-        if (hh < 3) s = cin[hh * H2 + i2];
-        const int g_lo = max(hr, 0), g_hi = min(hr + 3, last_g);
-        for (int gi = g_lo; gi <= g_hi; ++gi) {
-          const C v = buf[gi * BUF + fft_pad((hr - gi + 3) * H2 + i2)];
-          s.x += v.x;
-          s.y += v.y;
-        }
-        const bool complete = min(hr + 3, last_needed_cap) <= last_g;
-        if (complete) {
-          const int hrel = fb + hr;  // hop relative to a
-          if (hrel < nhop) {
-            const long long o = (a + hrel) * H + 2 * i2;
-            if (o + 1 < tr.n) {
-              *reinterpret_cast<float2*>(tr.out + o) = s;
-            } else if (o < tr.n) {
-              tr.out[o] = s.x;
-            }
+    // ---- overlap-add, atomics-free and in a fixed order.  Hop h = samples [hH, (h+1)H) is
+    //      ((y_h[3] + y_{h+1}[2]) + y_{h+2}[1]) + y_{h+3}[0]  (y_f[q] = quarter q of frame f).
+    //      Every thread owns output columns (float2 at 2*i2 inside the hop) for the whole chunk and
+    //      keeps the three pending partial sums in registers; frames arrive in ascending order:
+    //        emit hop f-3 = p0 + y_f[0];  p0 = p1 + y_f[1];  p1 = p2 + y_f[2];  p2 = y_f[3]
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int i2 = tid + c * THREADS;
+      if (i2 < H2) {
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          if (gi < nfr) {
+            const C* yb = buf + gi * BUF;
+            const C q0 = yb[fft_pad(i2)], q1 = yb[fft_pad(H2 + i2)];
+            const C q2 = yb[fft_pad(2 * H2 + i2)], q3 = yb[fft_pad(3 * H2 + i2)];
+            const float2 o = make_float2(p0[c].x + q0.x, p0[c].y + q0.y);
+            p0[c] = make_float2(p1[c].x + q1.x, p1[c].y + q1.y);
+            p1[c] = make_float2(p2[c].x + q2.x, p2[c].y + q2.y);
+            p2[c] = make_float2(q3.x, q3.y);
+            emit_hop(fb + gi - 3, i2, o);
           }
-        } else {
-          cout[(hh - G) * H2 + i2] = s;
         }
       }
-      cb ^= 1;
     }
     __syncthreads();
+  }
+  // hops whose later frames do not exist (end of the track): what has been summed is the result
+  const int last = nfr_total - 1;
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    const int i2 = tid + c * THREADS;
+    if (i2 < H2) {
+      emit_hop(last - 2, i2, p0[c]);
+      emit_hop(last - 1, i2, p1[c]);
+      emit_hop(last, i2, p2[c]);
+    }
   }
 }
 
