@@ -257,15 +257,23 @@ struct Fft {
   using C = cplx<T>;
   static constexpr int TPF = P::TPF;
 
+  // Padded address of element (t + m*TPF): TPF is a multiple of 16, so the padding term splits
+  // exactly, pad(t + m*TPF) = pad(t) + m*(TPF + TPF/16) -- one base pointer per thread and
+  // compile-time offsets instead of address arithmetic per access.
+  static constexpr int SLOT_STRIDE = TPF + TPF / 16;
+  static_assert(TPF % 16 == 0, "slot stride needs TPF to be a multiple of 16");
+
   // load slot m <- buf[t + m*TPF]
   static MLX_HD void load(C (&x)[16], const C* buf, int t) {
+    const C* p = buf + fft_pad(t);
 #pragma unroll
-    for (int m = 0; m < 16; ++m) x[m] = buf[fft_pad(t + m * TPF)];
+    for (int m = 0; m < 16; ++m) x[m] = p[m * SLOT_STRIDE];
   }
   // store slot m -> buf[t + m*TPF]
   static MLX_HD void store(const C (&x)[16], C* buf, int t) {
+    C* p = buf + fft_pad(t);
 #pragma unroll
-    for (int m = 0; m < 16; ++m) buf[fft_pad(t + m * TPF)] = x[m];
+    for (int m = 0; m < 16; ++m) p[m * SLOT_STRIDE] = x[m];
   }
 
   // butterflies of stage S on the register slots; non-last stages scatter to buf, the last stage
@@ -288,8 +296,13 @@ struct Fft {
         const int j = t + b * TPF;
         const int k = j & (NS - 1);
         const int j0 = (j - k) * R + k;
+        // pad(j0 + r*NS): for NS = 1 (first stage) j0 = 16 j and r < 16 stay inside one padding
+        // block; for NS a multiple of 16 the padding term splits exactly.
+        C* p = buf + fft_pad(j0);
+        constexpr int RS = (NS % 16 == 0) ? NS + NS / 16 : NS;
+        static_assert(NS % 16 == 0 || (NS == 1 && R == 16), "unsupported stage geometry");
 #pragma unroll
-        for (int r = 0; r < R; ++r) buf[fft_pad(j0 + r * NS)] = v[r];
+        for (int r = 0; r < R; ++r) p[r * RS] = v[r];
       }
     }
   }
