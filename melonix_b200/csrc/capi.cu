@@ -593,15 +593,35 @@ int mlx_spec_frames_dev(mlx_ctx* c, int track, int fftN, int hop, int64_t first_
   return spec_common(c, track, fftN, nullptr, hop, first_frame, count, out_dev, nullptr, 0.f);
 }
 
+// A host job list that is a run of consecutive frames of one hop -- jobs[i] = (s0 + i*hop,
+// s0 + (i+1)*hop) with s0 a multiple of hop, which is what SpecCache::populateTex produces at a fixed
+// zoom (spec-cache.cpp:63-65) -- is handed to the kernels in regular-hop form, so that launch_spec can
+// pick the tiled kernel; any other list stays a list.
+static bool regular_run(const int32_t* se, int count, int* hop, int64_t* first_frame) {
+  const int64_t h = (int64_t)se[1] - se[0];
+  if (h <= 0 || se[0] < 0 || se[0] % h != 0) return false;
+  for (int i = 0; i < count; ++i)
+    if (se[2 * i] != se[0] + i * h || se[2 * i + 1] != se[2 * i] + h) return false;
+  *hop = (int)h;
+  *first_frame = se[0] / h;
+  return true;
+}
+
 int mlx_spec_batch(mlx_ctx* c, int track, int fftN, const int32_t* start_end, int count, float* out) {
   if (!c || !start_end || !out) return fail(MLX_ERR_INVALID, "null argument");
   if (count <= 0) return count == 0 ? MLX_OK : fail(MLX_ERR_INVALID, "count < 0");
   CK(cudaSetDevice(c->device));
   CK(c->jobs.reserve(sizeof(int32_t) * 2 * (size_t)count));
   CK(c->spec_out.reserve(sizeof(float) * (size_t)count * (fftN / 2)));
-  CK(cudaMemcpyAsync(c->jobs.p, start_end, sizeof(int32_t) * 2 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
-  int rc = spec_common(c, track, fftN, static_cast<const int*>(c->jobs.p), 0, 0, count,
-                       static_cast<float*>(c->spec_out.p), nullptr, 0.f);
+  int hop = 0, rc;
+  int64_t first = 0;
+  if (regular_run(start_end, count, &hop, &first)) {
+    rc = spec_common(c, track, fftN, nullptr, hop, first, count, static_cast<float*>(c->spec_out.p), nullptr, 0.f);
+  } else {
+    CK(cudaMemcpyAsync(c->jobs.p, start_end, sizeof(int32_t) * 2 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    rc = spec_common(c, track, fftN, static_cast<const int*>(c->jobs.p), 0, 0, count,
+                     static_cast<float*>(c->spec_out.p), nullptr, 0.f);
+  }
   if (rc) return rc;
   CK(cudaMemcpyAsync(out, c->spec_out.p, sizeof(float) * (size_t)count * (fftN / 2), cudaMemcpyDeviceToHost,
                      c->stream));
@@ -617,9 +637,15 @@ int mlx_spec_batch_rgb(mlx_ctx* c, int track, int fftN, const int32_t* start_end
   const size_t bytes = (size_t)count * (fftN / 2) * 3;
   CK(c->jobs.reserve(sizeof(int32_t) * 2 * (size_t)count));
   CK(c->spec_rgb.reserve(bytes));
-  CK(cudaMemcpyAsync(c->jobs.p, start_end, sizeof(int32_t) * 2 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
-  int rc = spec_common(c, track, fftN, static_cast<const int*>(c->jobs.p), 0, 0, count, nullptr,
-                       static_cast<unsigned char*>(c->spec_rgb.p), k);
+  int hop = 0, rc;
+  int64_t first = 0;
+  if (regular_run(start_end, count, &hop, &first)) {
+    rc = spec_common(c, track, fftN, nullptr, hop, first, count, nullptr, static_cast<unsigned char*>(c->spec_rgb.p), k);
+  } else {
+    CK(cudaMemcpyAsync(c->jobs.p, start_end, sizeof(int32_t) * 2 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    rc = spec_common(c, track, fftN, static_cast<const int*>(c->jobs.p), 0, 0, count, nullptr,
+                     static_cast<unsigned char*>(c->spec_rgb.p), k);
+  }
   if (rc) return rc;
   CK(cudaMemcpyAsync(out_rgb, c->spec_rgb.p, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));

@@ -25,12 +25,19 @@
 
 #include "fft.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 #ifndef MLX_UNROLL_PAIR
 #define MLX_UNROLL_PAIR 2
 #endif
 #ifndef MLX_UNROLL_GATHER
 #define MLX_UNROLL_GATHER 2
+#endif
+#ifndef MLX_GATHER_V2
+#define MLX_GATHER_V2 1  // constant-rate bin shift with frame-invariant constants (bit-identical to v1)
+#endif
+#ifndef MLX_KA_CTAS
+#define MLX_KA_CTAS 1  // analysis CTAs per SM: 1 x 512 threads or 2 x 256 threads (same frames in flight)
 #endif
 
 namespace mlx {
@@ -52,7 +59,7 @@ struct PvCfg {
   static constexpr int QP = (NC / 2 + THREADS - 1) / THREADS;      // pair slots per thread (k = 1..NC/2)
   static constexpr int QB = (NC + THREADS - 1) / THREADS;          // bin slots per thread (bins 0..NC-1; bin NC: last warp)
   static constexpr bool WIN_D = (N <= 2048);                       // double window staged in smem
-  static constexpr int BUFS = BUF + 1;                             // + one slot for the Nyquist bin's (mag, d)
+  static constexpr int BUFS = BUF + 2;  // + the Nyquist bin's (mag, d) record + an all-zero record (empty K_j)
   static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUFS + (WIN_D ? sizeof(double) * N : 0) +
                                    sizeof(float) * 2 * TILE + 64;
   static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + 64;
@@ -63,7 +70,7 @@ struct PvCfg {
 template <int N>
 struct PvG {
   static constexpr int value = 8192 / N;    // K_S
-  static constexpr int analyze = 16384 / N; // K_A
+  static constexpr int analyze = (16384 / MLX_KA_CTAS) / N; // K_A
 };
 
 // what the pair phase leaves for the gather phase, stored in the first 8 bytes of the bin's (dead)
@@ -94,36 +101,6 @@ __device__ __forceinline__ GroupBar<TPF> make_group_bar(int g, int tid) {
   unsigned mask = 0xffffffffu;
   if constexpr (TPF < 32) mask = ((1u << TPF) - 1u) << (((tid & 31) / TPF) * TPF);
   return GroupBar<TPF>{1 + g, mask};
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -236,7 +213,7 @@ __device__ __noinline__ void gather_entry_slow(int j, float r, int NC, uint32_t&
 template <int NC, int BUF>
 __device__ __forceinline__ float shift_one_bin(const cplx<double>* zb, int j, uint32_t kk, uint32_t r_fix,
                                                uint32_t& inc) {
-  // fft_pad(NC) == BUF - 1: the extra slot of the Nyquist bin is where the padding formula puts it
+  // fft_pad(NC) is the first extra slot of the frame buffer: the Nyquist bin needs no special case
   auto magd = [&](int k) { return *reinterpret_cast<const MagD*>(zb + fft_pad(k)); };
   const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
   const bool any = klo <= khi;  // K_j non-empty (at most one bin when rate >= 1)
@@ -257,6 +234,44 @@ __device__ __forceinline__ float shift_one_bin(const cplx<double>* zb, int j, ui
       (unsigned long long)r_fix * nlo + ((unsigned long long)(r_fix * nhi) << 32) + (1ULL << 25);
   inc = any ? (uint32_t)(prod >> 26) : (((uint32_t)j & 3u) << 30);  // empty K_j: s_nu = j -> frac(j / 4)
   return smag;
+}
+
+// Frame-invariant part of the bin shift of one output bin j at a constant rate (MLX_GATHER_V2).
+// With K_j = [klo, khi], kh = khi and d' the signed phase advance (d32, -+2^32 on a cut flip)
+//     inc = (r_fix * (kh * 2^30 + d') + 2^25) >> 26   (mod 2^32)
+// is a product in the ring of integers mod 2^64, so the kh term is added once per launch:
+//     base = r_fix * kh * 2^30 + 2^25,   inc = (base + r_eff * d') >> 26.
+// An empty K_j (s_nu = j, inc = frac(j / 4) * 2^32, smag = 0) is the same formula with
+// base = (j & 3) << 56 (+ 2^25, which the shift drops) reading an all-zero (mag, d) record.  The
+// result is bit-identical to shift_one_bin(); the per-frame work is one 32 x 32 + 64 multiply-add,
+// the flip term and the shift.
+struct ShiftConst {
+  uint32_t slot;  // padded index of bin kh's (mag, d) record inside a frame buffer, or the zero record
+  unsigned long long base;
+};
+__device__ __forceinline__ ShiftConst make_shift_const(int j, uint32_t kk, uint32_t r_fix, int zero_slot) {
+  const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
+  ShiftConst c;
+  if (klo <= khi) {
+    c.slot = (uint32_t)fft_pad(khi);
+    c.base = (unsigned long long)r_fix * ((unsigned long long)khi << 30) + (1ULL << 25);
+  } else {  // reads (mag, d) = (0, 0): smag = 0 and the product term vanishes
+    c.slot = (uint32_t)zero_slot;
+    c.base = ((unsigned long long)((uint32_t)j & 3u) << 56) + (1ULL << 25);
+  }
+  return c;
+}
+// one frame of one output bin whose K_j has at most one element (rate >= 1)
+__device__ __forceinline__ float shift_one_bin_v2(const cplx<double>* zb, const ShiftConst& c, int r_fix,
+                                                  uint32_t& inc) {
+  const MagD mh = *reinterpret_cast<const MagD*>(zb + c.slot);
+  const uint32_t mb = __float_as_uint(mh.mag);
+  // cut flip (sign bit of the stored magnitude): d' = d32 + 2^32 when d32 < 0, d32 - 2^32 otherwise
+  const int hi_adj = ((int)mb >> 31) & (mh.d < 0 ? r_fix : -r_fix);
+  unsigned long long prod = c.base + (unsigned long long)((long long)mh.d * (long long)r_fix);
+  prod += (unsigned long long)(uint32_t)hi_adj << 32;
+  inc = (uint32_t)(prod >> 26);
+  return __uint_as_float(mb & 0x7fffffffu);
 }
 
 // sin/cos of 2*pi*acc/2^32: the quadrant comes from the top bits (exact range reduction for free),
@@ -287,7 +302,7 @@ __device__ __forceinline__ void sincos_turns(uint32_t acc, float& s, float& c) {
 // ------------------------------------------------------------------------------------------------
 // K_A
 template <int N, int G>
-__global__ void __launch_bounds__(PvCfg<N, G>::THREADS, 1)
+__global__ void __launch_bounds__(PvCfg<N, G>::THREADS, MLX_KA_CTAS)
 pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = PvCfg<N, G>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NB = Cfg::NB, NBP = Cfg::NBP;
@@ -301,7 +316,8 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   double* s_win = reinterpret_cast<double*>(buf + G * BUF);       // [N] when WD
   float* tile = reinterpret_cast<float*>(s_win + (WD ? N : 0));   // [2][TILE]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + 2 * TILE);  // [2]
-  static_assert(fft_pad(NC) == BUF - 1, "the Nyquist bin's (mag, d) record uses the extra slot");
+  static_assert(fft_pad(NC) == BUF - 2, "the Nyquist bin's (mag, d) record uses the first extra slot");
+  constexpr int ZSLOT = BUF - 1;  // (mag, d) = (0, 0): what an empty K_j reads
   auto slot = [](int k) { return fft_pad(k); };
 
   const int tid = threadIdx.x;
@@ -368,6 +384,14 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     gkq[q] = (!per_frame_rate && j < NC) ? __ldg(wv.gk + j) : 1u;
   }
   const uint32_t gk_nyq = per_frame_rate ? 1u : __ldg(wv.gk + NC);
+#if MLX_GATHER_V2
+  // rate >= 1: every K_j holds at most one bin and the shift of a bin is a handful of integer ops
+  const bool fast_shift = !per_frame_rate && wv.rate >= 1.0f;
+  ShiftConst scq[QB];
+#pragma unroll
+  for (int q = 0; q < QB; ++q) scq[q] = make_shift_const(tid + q * THREADS, gkq[q], (uint32_t)wv.r_fix, ZSLOT);
+  for (int gg = tid; gg < G; gg += THREADS) buf[gg * BUF + ZSLOT] = C{0.0, 0.0};  // visible after the first barrier
+#endif
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
   const size_t row0 = (size_t)blockIdx.y * wv.rows;
 
@@ -443,7 +467,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         const MagD mn = analysis_real_bin(z0.x - z0.y, ppn, pmn);
         if (emit) {
           *reinterpret_cast<MagD*>(zb) = m0;
-          *reinterpret_cast<MagD*>(zb + BUF - 1) = mn;
+          *reinterpret_cast<MagD*>(zb + fft_pad(NC)) = mn;
         }
       }
     }
@@ -468,12 +492,20 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         const int j = tid + q * THREADS;
         if (j < NC) {
           uint32_t kk, inc;
-          if (per_frame_rate) {
-            gather_entry_slow(j, r, NC, kk);
-          } else {
-            kk = gkq[q];
+          float smag;
+#if MLX_GATHER_V2
+          if (fast_shift) {
+            smag = shift_one_bin_v2(zb, scq[q], (int)r_fix, inc);
+          } else
+#endif
+          {
+            if (per_frame_rate) {
+              gather_entry_slow(j, r, NC, kk);
+            } else {
+              kk = gkq[q];
+            }
+            smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
           }
-          const float smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
           lacc[q] += inc;
           if (counted) totc[q] = lacc[q];
           sc.smag[row + j] = smag;
@@ -827,6 +859,11 @@ static cudaError_t configure_n() {
   cudaError_t e = cudaFuncSetAttribute(pv_analyze_kernel<N, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)PvCfg<N, GA>::SMEM_A);
   if (e != cudaSuccess) return e;
+  // the analysis kernel lives on shared memory: ask for the largest carve-out so that MLX_KA_CTAS
+  // CTAs are resident
+  e = cudaFuncSetAttribute(pv_analyze_kernel<N, GA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(pv_synth_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)PvCfg<N, G>::SMEM_S);
 }
@@ -846,15 +883,15 @@ cudaError_t pv_configure(int fftN) {
   return cudaSuccess;
 }
 int pv_group_count(int fftN) { return 8192 / fftN; }
-int pv_group_count_analyze(int fftN) { return 16384 / fftN; }
+int pv_group_count_analyze(int fftN) { return (16384 / MLX_KA_CTAS) / fftN; }
 int pv_threads(int) { return 256; }
 size_t pv_analyze_smem(int fftN) {
   switch (fftN) {
-    case 512: return PvCfg<512, 32>::SMEM_A;
-    case 1024: return PvCfg<1024, 16>::SMEM_A;
-    case 2048: return PvCfg<2048, 8>::SMEM_A;
-    case 4096: return PvCfg<4096, 4>::SMEM_A;
-    case 8192: return PvCfg<8192, 2>::SMEM_A;
+    case 512: return PvCfg<512, PvG<512>::analyze>::SMEM_A;
+    case 1024: return PvCfg<1024, PvG<1024>::analyze>::SMEM_A;
+    case 2048: return PvCfg<2048, PvG<2048>::analyze>::SMEM_A;
+    case 4096: return PvCfg<4096, PvG<4096>::analyze>::SMEM_A;
+    case 8192: return PvCfg<8192, PvG<8192>::analyze>::SMEM_A;
   }
   return 0;
 }

@@ -1,0 +1,82 @@
+// melonix_b200/csrc/spec_frame.cuh -- per-thread pieces of the regular-hop Spec kernel (K1r).
+//
+// One frame of Spec::internalGetSpec (reference spec.cpp:44-66) is transformed by a group of
+// TPF = N/32 threads as an N/2-point complex FFT of the even/odd packed real frame.  The three
+// per-thread steps around the FFT live here as host/device functions so that the same code is
+// compiled by g++ and run under a sequential emulation of the thread group against the oracle
+// (tests/host/spec_frame_emul.cpp) -- the index arithmetic is verified without a GPU.
+#pragma once
+#include <math.h>
+
+#include "fft.cuh"
+
+namespace mlx {
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float spec_sqrt(float x) {  // sqrt.approx: ~1 ulp, far inside the 1e-4 RMS budget
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float spec_mul(float a, float b) { return __fmul_rn(a, b); }
+#else
+inline float spec_sqrt(float x) { return __builtin_sqrtf(x); }
+inline float spec_mul(float a, float b) { return a * b; }
+#endif
+
+template <int N>
+struct SpecFrame {
+  static constexpr int NC = N / 2;
+  static constexpr int TPF = NC / 16;
+  using C = cplx<float>;
+  using F = Fft<float, NC, -1>;
+
+  // Window [end-N, end) of the frame, already in `cur` (zero outside the track): slot m takes the
+  // samples p = 2(t + m*TPF), p + 1, each multiplied by its window factor -- expf(-2.5e-4f*(start-i))
+  // before `start`, 1 from `start` on (spec.cpp:55-58; the float product is the reference's own).
+  // win2(p) returns the factors of positions p and p + 1.
+  template <class Win2>
+  static MLX_HD void load(C (&x)[16], const float* cur, int t, Win2&& win2) {
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int p = 2 * (t + m * TPF);
+      const C s2 = *reinterpret_cast<const C*>(cur + p);
+      const C w2 = win2(p);
+      x[m] = C{spec_mul(w2.x, s2.x), spec_mul(w2.y, s2.y)};
+    }
+  }
+
+  // After the FFT x[m] = Z[t + m*TPF].  Bin k = t + q*TPF (q < 8) pairs with bin NC - k, which is
+  // slot 15 - q (16 - q for t = 0) of thread (TPF - t) mod TPF: only the upper slots are exchanged.
+  static MLX_HD void stage_upper(const C (&x)[16], C* buf, int t) {
+    C* p = buf + fft_pad(t);
+#pragma unroll
+    for (int m = 8; m < 16; ++m) p[m * F::SLOT_STRIDE] = x[m];
+  }
+
+  // |X[k]| / N for the bins of this thread: X[k] = E[k] + W^k O[k] from Z[k] and Z[NC-k]; the split
+  // works on 2X, `scale` = 0.5 / N.  emit(k, value) is called for every k in [0, NC) exactly once
+  // over the group; the Nyquist bin X[NC] is dropped as the reference does (spec.cpp:61).
+  template <class Twr, class Emit>
+  static MLX_HD void emit_bins(const C (&x)[16], const C* buf, int t, float scale, Twr&& twr, Emit&& emit) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k = t + q * TPF;
+      const C za = x[q];
+      C zc = buf[fft_pad((NC - k) & (NC - 1))];
+      if (q == 0 && t == 0) zc = za;  // Z[NC] == Z[0] (slot 0 is not staged)
+      const C w = twr(k);             // exp(-2 pi i k / N)
+      const float er = za.x + zc.x, ei = za.y - zc.y;
+      const float dr = za.x - zc.x, di = za.y + zc.y;
+      const float tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
+      const float xkr = er + ti_, xki = ei - tr_;
+      const float xmr = er - ti_, xmi = -ei - tr_;
+      emit(k, spec_sqrt(fmaf(xkr, xkr, xki * xki)) * scale);
+      if (q != 0 || t != 0) emit(NC - k, spec_sqrt(fmaf(xmr, xmr, xmi * xmi)) * scale);
+    }
+    // |X[NC/2]| = |Z[NC/2]|, slot 8 of thread 0
+    if (t == 0) emit(NC / 2, spec_sqrt(fmaf(x[8].x, x[8].x, x[8].y * x[8].y)) * (2.f * scale));
+  }
+};
+
+}  // namespace mlx

@@ -8,9 +8,12 @@
 // memory (fft.cuh) and many jobs are in flight per launch.  K7 (optional) fuses the colour ramp of
 // SpecCache::populateTex (reference spec-cache.cpp:77-96) into the epilogue.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "fft.cuh"
 #include "kernels.h"
+#include "spec_frame.cuh"
+#include "tma.cuh"
 
 namespace mlx {
 
@@ -39,13 +42,6 @@ struct SpecBar {
     }
   }
 };
-
-// sqrt.approx: ~1 ulp, far inside the 1e-4 RMS budget of the float magnitudes
-__device__ __forceinline__ float spec_sqrt(float x) {
-  float y;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // colour ramp, reference spec-cache.cpp:79-96 (note 255/3 == 85 and 2*255/3 == 170: int division)
 __device__ __forceinline__ void colour_ramp(float v, float k, unsigned char* rgb) {
@@ -178,6 +174,130 @@ spec_kernel(const SpecArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1r: the regular-hop form of K1 (job f = (start = f*hop, end = start + hop), the geometry
+// SpecCache::populateTex produces at a fixed zoom, spec-cache.cpp:63-65).  Consecutive frames share
+// N - hop samples, so a CTA takes a run of consecutive frames and stages one contiguous sample tile
+// per batch of JPB frames with a 1-D TMA bulk copy (double-buffered: the copy of batch b+2 is in
+// flight while batch b is transformed).  The window factor depends only on the position inside the
+// frame (distance to `start` = N - hop - p), so it is one shared-memory table and one float product
+// per sample -- exactly the product of spec.cpp:58 -- and the zero padding kept around every track
+// in HBM replaces the bounds tests of spec.cpp:50-54.  The last FFT stage leaves Z in registers;
+// only the upper half of the slots goes through shared memory to reach the thread that owns the
+// mirrored bin.
+template <int N>
+struct SpecFramesCfg {
+  static constexpr int NC = N / 2;
+  static constexpr int TPF = NC / 16;
+  static constexpr int THREADS = 256;
+  static constexpr int JPB = THREADS / TPF;
+  static constexpr int BUF = FftPlan<NC>::BUF;
+  static constexpr bool TAB = (N <= 2048);  // window + split-twiddle tables staged in shared memory
+  static constexpr int TWR = ((NC / 2 + 1) + 1) & ~1;
+  static_assert(TPF <= THREADS, "regular-hop Spec kernel: fftN <= 8192");
+  static size_t smem(int hop) {
+    return sizeof(cplx<float>) * JPB * BUF + (TAB ? sizeof(float) * N + sizeof(cplx<float>) * TWR : 0) +
+           sizeof(float) * 2 * (size_t)(N + (JPB - 1) * hop) + 16;
+  }
+};
+
+template <int N, bool RGB>
+__global__ void __launch_bounds__(256, MLX_SPEC_MINB)
+spec_frames_kernel(const SpecArgs a, const int fpc) {
+  using Cfg = SpecFramesCfg<N>;
+  constexpr int NC = Cfg::NC, TPF = Cfg::TPF, JPB = Cfg::JPB, BUF = Cfg::BUF, THREADS = Cfg::THREADS;
+  constexpr bool TAB = Cfg::TAB;
+  using C = cplx<float>;
+  using SF = SpecFrame<N>;
+  using F = typename SF::F;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  C* bufs = reinterpret_cast<C*>(smem_raw);                               // [JPB][BUF]
+  float* s_win = reinterpret_cast<float*>(bufs + JPB * BUF);              // [N]         (TAB)
+  C* s_twr = reinterpret_cast<C*>(s_win + (TAB ? N : 0));                 // [TWR]       (TAB)
+  float* tile = reinterpret_cast<float*>(s_twr + (TAB ? Cfg::TWR : 0));   // [2][span]
+  const int hop = a.hop;
+  const int span = N + (JPB - 1) * hop;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + 2 * span);          // [2]
+
+  const int tid = threadIdx.x;
+  const int g = tid / TPF, t = tid % TPF;
+  const long long f_begin = (long long)blockIdx.x * fpc;
+  if (f_begin >= a.count) return;
+  const int nfr = (int)min((long long)fpc, a.count - f_begin);
+  const int nbatch = (nfr + JPB - 1) / JPB;
+  // first sample of the tile of batch b: window start of its first frame, (f + 1) * hop - N
+  const float* src0 = a.x + (a.first_frame + f_begin + 1) * hop - N;
+  const uint32_t tile_bytes = (uint32_t)span * sizeof(float);
+
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar + 1, 1);
+  }
+  const int ndec = N - hop;  // samples of the frame that lie before `start`
+  if constexpr (TAB) {
+    for (int p = tid; p < N; p += THREADS) s_win[p] = p < ndec ? a.decay[ndec - p] : 1.f;
+    for (int k = tid; k <= NC / 2; k += THREADS) s_twr[k] = a.twr_f[k];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(mbar, tile_bytes);
+    tma_load_1d(tile, src0, tile_bytes, mbar);
+    if (nbatch > 1) {
+      mbar_expect_tx(mbar + 1, tile_bytes);
+      tma_load_1d(tile + span, src0 + (long long)JPB * hop, tile_bytes, mbar + 1);
+    }
+  }
+
+  C* buf = bufs + g * BUF;
+  FftTwiddles<float, NC, -1> twd;
+  twd.init(t, a.tw_f);
+  unsigned mask = 0xffffffffu;
+  if constexpr (TPF < 32) mask = ((1u << TPF) - 1u) << (((tid & 31) / TPF) * TPF);
+  const SpecBar<TPF> bar{1 + g, mask};
+  const float scale = 0.5f / (float)N;  // the pair split below works on 2 X
+
+  for (int b = 0; b < nbatch; ++b) {
+    const int fr = b * JPB + g;
+    const bool active = fr < nfr;
+    mbar_wait(mbar + (b & 1), (b >> 1) & 1);
+    C x[16];
+    if (active) {
+      const float* cur = tile + (b & 1) * span + g * hop;
+      if constexpr (TAB) {
+        SF::load(x, cur, t, [&](int p) { return *reinterpret_cast<const C*>(s_win + p); });
+      } else {
+        SF::load(x, cur, t, [&](int p) {
+          return C{p < ndec ? __ldg(a.decay + (ndec - p)) : 1.f, p + 1 < ndec ? __ldg(a.decay + (ndec - p - 1)) : 1.f};
+        });
+      }
+    }
+    __syncthreads();  // every group has taken its samples out of tile (b & 1); previous epilogue reads done
+    if (tid == 0 && b + 2 < nbatch) {
+      mbar_expect_tx(mbar + (b & 1), tile_bytes);
+      tma_load_1d(tile + (b & 1) * span, src0 + (long long)(b + 2) * JPB * hop, tile_bytes, mbar + (b & 1));
+    }
+    if (!active) continue;
+    F::run(x, buf, t, twd, bar);
+    SF::stage_upper(x, buf, t);
+    bar.sync();
+    const long long frame = f_begin + fr;
+    float* out = a.out ? a.out + frame * NC : nullptr;
+    unsigned char* rgb = RGB ? a.rgb + frame * NC * 3 : nullptr;
+    auto twr = [&](int k) {
+      if constexpr (TAB) {
+        return s_twr[k];
+      } else {
+        const float2 wv = __ldg(reinterpret_cast<const float2*>(a.twr_f + k));
+        return C{wv.x, wv.y};
+      }
+    };
+    SF::emit_bins(x, buf, t, scale, twr, [&](int k, float v) {
+      if (out) out[k] = v;
+      if constexpr (RGB) colour_ramp(v, a.kcol, rgb + 3 * k);
+    });
+  }
+}
+
 #define MLX_SPEC_DISPATCH(N_, ...)                           \
   switch (N_) {                                              \
     case 512: { constexpr int N = 512; __VA_ARGS__; } break;     \
@@ -190,14 +310,85 @@ spec_kernel(const SpecArgs a) {
     default: return cudaErrorInvalidValue;                   \
   }
 
+#define MLX_SPECR_DISPATCH(N_, ...)                          \
+  switch (N_) {                                              \
+    case 512: { constexpr int N = 512; __VA_ARGS__; } break;     \
+    case 1024: { constexpr int N = 1024; __VA_ARGS__; } break;   \
+    case 2048: { constexpr int N = 2048; __VA_ARGS__; } break;   \
+    case 4096: { constexpr int N = 4096; __VA_ARGS__; } break;   \
+    case 8192: { constexpr int N = 8192; __VA_ARGS__; } break;   \
+    default: return cudaErrorInvalidValue;                   \
+  }
+
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+template <int N, bool RGB>
+static cudaError_t configure_frames() {
+  size_t m = SpecFramesCfg<N>::smem(N);  // hop <= N
+  if (m > kMaxDynSmem) m = kMaxDynSmem;
+  return cudaFuncSetAttribute(spec_frames_kernel<N, RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m);
+}
+
 cudaError_t spec_configure(int fftN) {
-  MLX_SPEC_DISPATCH(fftN, return cudaFuncSetAttribute(spec_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                      (int)SpecCfg<N>::SMEM));
+  MLX_SPEC_DISPATCH(fftN, {
+    cudaError_t e = cudaFuncSetAttribute(spec_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SpecCfg<N>::SMEM);
+    if (e != cudaSuccess) return e;
+  });
+  if (fftN <= 8192) {
+    MLX_SPECR_DISPATCH(fftN, {
+      cudaError_t e = configure_frames<N, false>();
+      if (e != cudaSuccess) return e;
+      return configure_frames<N, true>();
+    });
+  }
   return cudaSuccess;
+}
+
+// Regular-hop launches go to K1r when its tiles are aligned for TMA and stay inside the zero padding
+// of the track; everything else (arbitrary job lists, odd hops such as the reference's 375-sample
+// pixel, fftN > 8192) takes the general kernel.
+static bool spec_frames_eligible(int fftN, const SpecArgs& a) {
+  static const bool off = getenv("MLX_SPEC_GENERIC") != nullptr;
+  if (off || a.jobs != nullptr || fftN > 8192) return false;
+  if (a.hop <= 0 || a.hop > fftN || (a.hop & 3) != 0 || a.first_frame < 0) return false;
+  const int jpb = 256 / (fftN / 32);
+  if ((a.first_frame + a.count + jpb) * (long long)a.hop > a.n + kPadBack) return false;
+  return true;
+}
+
+template <int N>
+static cudaError_t launch_spec_frames(const SpecArgs& a, cudaStream_t st) {
+  using Cfg = SpecFramesCfg<N>;
+  const size_t smem = Cfg::smem(a.hop);
+  if (smem > kMaxDynSmem) return cudaErrorInvalidConfiguration;
+  int dev = 0, sms = 148, occ = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (a.rgb) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spec_frames_kernel<N, true>, Cfg::THREADS, smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spec_frames_kernel<N, false>, Cfg::THREADS, smem);
+  if (occ < 1) occ = 1;
+  // frames per CTA: whole batches, at most 32 of them, and a grid that fills the resident slots evenly
+  const long long batches = (a.count + Cfg::JPB - 1) / Cfg::JPB;
+  const long long slots = (long long)sms * occ;
+  const long long rounds = (batches + slots * 32 - 1) / (slots * 32);
+  long long nb = (batches + slots * rounds - 1) / (slots * rounds);
+  if (nb < 1) nb = 1;
+  const int fpc = (int)nb * Cfg::JPB;
+  const int grid = (int)((a.count + fpc - 1) / fpc);
+  if (a.rgb) spec_frames_kernel<N, true><<<grid, Cfg::THREADS, smem, st>>>(a, fpc);
+  else spec_frames_kernel<N, false><<<grid, Cfg::THREADS, smem, st>>>(a, fpc);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_spec(int fftN, const SpecArgs& a, cudaStream_t st) {
   if (a.count <= 0) return cudaSuccess;
+  if (spec_frames_eligible(fftN, a)) {
+    cudaError_t e = cudaErrorInvalidConfiguration;
+    MLX_SPECR_DISPATCH(fftN, e = launch_spec_frames<N>(a, st));
+    if (e != cudaErrorInvalidConfiguration) return e;
+    (void)cudaGetLastError();
+  }
   MLX_SPEC_DISPATCH(fftN, {
     using Cfg = SpecCfg<N>;
     int dev = 0, sms = 148, occ = 1;

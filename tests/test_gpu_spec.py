@@ -84,6 +84,48 @@ def test_regular_hop_device_path(engine, oracle):
     assert rms(out.cpu().numpy(), oracle.spec_batch(x, 2048, S.regular_jobs(x.size, 512))) < 1e-7
 
 
+@pytest.mark.parametrize("N", [512, 1024, 2048, 4096, 8192])
+def test_regular_hop_tiled_kernel(engine, oracle, N):
+    """K1r (TMA-tiled regular-hop kernel): hops N/4, N and a 300-sample "pixel", first_frame > 0,
+    frames that reach into the zero padding on both sides; against the oracle and against the
+    general job-list kernel on the same jobs."""
+    import torch
+    x = S.vibrato_tone(1.5, seed=3 * N)
+    engine.upload_tracks([x])
+    engine.use_torch_stream()
+    for hop, first in ((N // 4, 0), (N, 0), (300, 0), (N // 4, 7)):
+        if hop > N:
+            continue
+        F = (x.size + hop - 1) // hop + 5 - first          # five frames past the end of the track
+        out = torch.empty((F, N // 2), dtype=torch.float32, device="cuda")
+        engine.spec_frames_dev(0, N, hop, first, F, out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        f = np.arange(first, first + F)
+        jobs = np.stack([f * hop, (f + 1) * hop], 1).astype(np.int32)
+        ref = oracle.spec_batch(x, N, jobs)
+        assert rms(got, ref) < 1e-7 and np.abs(got - ref).max() < 1e-6, (N, hop, first)
+        perm = np.random.default_rng(N + hop).permutation(F)  # a shuffled list is not a regular run
+        gen = engine.spec_batch(0, N, jobs[perm])
+        assert np.abs(gen - got[perm]).max() < 1e-6, (N, hop, first)
+
+
+def test_regular_hop_many_batches(engine, oracle):
+    """K1r with several double-buffered tile batches per CTA (120 s, 1024/256: 22 500 frames) through
+    the host job-list entry point, which recognises the regular run."""
+    x = S.vibrato_tone(120.0, seed=77)
+    jobs = S.regular_jobs(x.size, 256)
+    engine.upload_tracks([x])
+    got = engine.spec_batch(0, 1024, jobs)
+    ref = oracle.spec_batch(x, 1024, jobs)
+    assert got.shape == ref.shape == (22500, 512)
+    assert rms(got, ref) < 1e-7 and np.abs(got - ref).max() < 1e-6
+    rgb = engine.spec_batch_rgb(0, 1024, jobs[:4000], 2.0 ** 12).astype(np.int32)
+    rref = oracle.colormap(ref[:4000], 2.0 ** 12).astype(np.int32)
+    d = np.abs(rgb - rref)
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
 def test_fused_colour_ramp(engine, oracle):
     """K7: RGB texels vs the oracle's restatement of spec-cache.cpp:77-96 applied to the oracle's
     spectrum.  Casts truncate, so a 1e-7 relative magnitude difference can move a texel by one."""

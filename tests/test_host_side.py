@@ -31,6 +31,23 @@ def test_device_fft_emulated_on_host(tmp_path):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
 
 
+def test_spec_frame_steps_emulated_on_host(tmp_path):
+    """Per-thread steps of the regular-hop Spec kernel (spec_frame.cuh) under a sequential thread-group
+    emulation, against the oracle restatement of spec.cpp:44-66."""
+    exe = tmp_path / "spec_frame_emul"
+    gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    objs = []
+    for c in ("spec_ref.c", "fft64.c"):
+        o = tmp_path / (c + ".o")
+        subprocess.run(["gcc", "-O2", "-fopenmp", "-c", str(ROOT / "oracle" / c), "-o", str(o)], check=True,
+                       capture_output=True)
+        objs.append(str(o))
+    subprocess.run([gxx, "-std=c++17", "-O2", str(ROOT / "tests/host/spec_frame_emul.cpp"), *objs, "-o", str(exe),
+                    "-lm", "-fopenmp"], check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
+
+
 def test_c_abi_exports_every_declared_symbol():
     from melonix_b200 import capi, hostlib
     L = capi.lib()

@@ -1,5 +1,6 @@
 #!/bin/bash
-# tools/build_variant.sh NAME "-DFLAG=.. -DFLAG2=.."  -> build/variants/NAME.so (kernel tuning experiments)
+# tools/build_variant.sh NAME "-DFLAG=.. -DFLAG2=.."  -> variants/NAME.so (kernel tuning experiments;
+# variants/ is git-ignored through *.so but travels to the GPU box, build/ does not)
 set -e
 cd "$(dirname "$0")/../melonix_b200/csrc"
 out=../../build/variants; mkdir -p $out/$1
@@ -7,5 +8,6 @@ for f in capi pv_kernels spec_kernels grain_kernels; do
   nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $2 -c $f.cu -o $out/$1/$f.o &
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o $out/$1.so $out/$1/*.o
-echo built $out/$1.so
+mkdir -p ../../variants
+nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o ../../variants/$1.so $out/$1/*.o
+echo built variants/$1.so
