@@ -141,6 +141,22 @@ MLX_API int mlx_grain_render(mlx_ctx *ctx, int track, const int32_t *g_start, co
                      const float *g_rate, const int64_t *out_off, const float *g_next, int ngrains,
                      int tail_zeros, float *out, int16_t *out_i16);
 
+/* ---- grain segmentation (replaces the zero-crossing search of App::preproc, reference
+ *      app.cpp:156-235: probes start+1500 +0,+0,+1,-1,...,-749 with look-around 7, app.cpp:164-181,
+ *      else forward scan from start+2250 with look-around 3, app.cpp:198-217) --------------------- */
+/* Segments EVERY uploaded track in one call: the crossing predicates are evaluated for all samples
+ * in parallel, the (serial, O(#grains)) chain runs one CTA per track.  Row t of g_start / g_len
+ * receives the first min(counts[t], cap) grains of track t as (start, length) -- the key and span
+ * size of the reference's `grains` map (app.hpp:40); counts[t] is the full grain count (call again
+ * with a larger cap if it exceeds cap; n/751 + 1 always suffices).  Same results as
+ * mlxh_grain_segment (include/melonix_host.h), bit for bit. */
+MLX_API int mlx_grain_segment(mlx_ctx *ctx, int32_t *const *g_start, int32_t *const *g_len, int cap,
+                      int32_t *counts);
+/* Same with device pointers (g_start_dev / g_len_dev: host arrays of ntracks device row pointers,
+ * counts_dev: device array of ntracks int32); asynchronous on the context stream. */
+MLX_API int mlx_grain_segment_dev(mlx_ctx *ctx, int32_t *const *g_start_dev, int32_t *const *g_len_dev,
+                          int cap, int32_t *counts_dev);
+
 #ifdef __cplusplus
 }
 #endif

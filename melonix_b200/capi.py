@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
     L.mlx_pv_process_host.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(i64), i32,
                                       C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mlx_grain_render.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    L.mlx_grain_segment.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32, vp]
+    L.mlx_grain_segment_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32, vp]
     _lib = L
     return L
 

@@ -100,6 +100,7 @@ struct mlx_ctx {
   DevBuf out_wav, out_peak, out_f0;  // device results for the host-pointer entry points
   DevBuf jobs, spec_out, spec_rgb;
   DevBuf g_i32a, g_i32b, g_f32a, g_f32b, g_i64, g_out, g_out16;
+  DevBuf seg_bits, seg_desc, seg_rows, seg_count;  // grain segmentation scratch
   // pinned staging ring for per-call descriptors / tables: a slot is reused only after the copies
   // that read it have completed (event), so launches never wait on the host.
   struct Slot {
@@ -455,7 +456,8 @@ void mlx_destroy(mlx_ctx* c) {
   cudaDeviceSynchronize();
   for (DevBuf* b : {&c->gk, &c->track_buf, &c->smag, &c->lacc, &c->tot, &c->totc, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
                     &c->out_wav, &c->out_peak, &c->out_f0, &c->jobs, &c->spec_out, &c->spec_rgb, &c->g_i32a,
-                    &c->g_i32b, &c->g_f32a, &c->g_f32b, &c->g_i64, &c->g_out, &c->g_out16})
+                    &c->g_i32b, &c->g_f32a, &c->g_f32b, &c->g_i64, &c->g_out, &c->g_out16, &c->seg_bits,
+                    &c->seg_desc, &c->seg_rows, &c->seg_count})
     b->release();
   for (auto& kv : c->tables)
     for (DevBuf* b : {&kv.second.tw_d, &kv.second.twr_d, &kv.second.tw_f, &kv.second.twr_f, &kv.second.win,
@@ -890,6 +892,86 @@ int mlx_grain_render(mlx_ctx* c, int track, const int32_t* g_start, const int32_
   if (out) CK(cudaMemcpyAsync(out, c->g_out.p, sizeof(float) * total, cudaMemcpyDeviceToHost, c->stream));
   if (out_i16)
     CK(cudaMemcpyAsync(out_i16, c->g_out16.p, sizeof(int16_t) * total, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+// Grain segmentation of every uploaded track (K8a crossings + K8b chain, grain_kernels.cu).
+// Row t of the outputs has `cap` entries; counts[t] may exceed cap (then only cap rows were written).
+static int grain_segment_common(mlx_ctx* c, int32_t* const* g_start_dev, int32_t* const* g_len_dev, int cap,
+                                int32_t* counts_dev) {
+  const int nt = (int)c->tracks.size();
+  // bit arrays: two per track, ceil(n / 32) + 1 words each, 16-byte aligned
+  std::vector<size_t> woff(nt + 1, 0);
+  long long max_words = 0;
+  for (int t = 0; t < nt; ++t) {
+    const long long nw = (c->tracks[t].n + 31) / 32 + 1;
+    max_words = std::max(max_words, nw);
+    woff[t + 1] = woff[t] + 2 * (size_t)((nw + 3) & ~3LL);
+  }
+  CK(c->seg_bits.reserve(sizeof(uint32_t) * std::max<size_t>(woff[nt], 4)));
+  CK(c->seg_desc.reserve(sizeof(GrainSegTrack) * nt));
+  mlx_ctx::Slot* slot = nullptr;
+  int rc = acquire_slot(c, sizeof(GrainSegTrack) * nt, &slot);
+  if (rc) return rc;
+  GrainSegTrack* d = static_cast<GrainSegTrack*>(slot->p);
+  uint32_t* bits = static_cast<uint32_t*>(c->seg_bits.p);
+  for (int t = 0; t < nt; ++t) {
+    const long long nw = (c->tracks[t].n + 31) / 32 + 1;
+    d[t].x = c->track_ptr(t);
+    d[t].n = c->tracks[t].n;
+    d[t].nwords = nw;
+    d[t].z7 = bits + woff[t];
+    d[t].z3 = bits + woff[t] + (size_t)((nw + 3) & ~3LL);
+    d[t].g_start = g_start_dev[t];
+    d[t].g_len = g_len_dev[t];
+    d[t].count = counts_dev + t;
+  }
+  CK(cudaMemcpyAsync(c->seg_desc.p, d, sizeof(GrainSegTrack) * nt, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(slot->done, c->stream));
+  c->mark(4);
+  CK(launch_grain_segment(static_cast<const GrainSegTrack*>(c->seg_desc.p), nt, max_words, cap, c->stream));
+  c->mark(-1);
+  c->launches += 2;
+  return MLX_OK;
+}
+
+int mlx_grain_segment_dev(mlx_ctx* c, int32_t* const* g_start_dev, int32_t* const* g_len_dev, int cap,
+                          int32_t* counts_dev) {
+  if (!c || !g_start_dev || !g_len_dev || !counts_dev || cap < 0) return fail(MLX_ERR_INVALID, "bad argument");
+  if (c->tracks.empty()) return fail(MLX_ERR_STATE, "no tracks uploaded");
+  for (size_t t = 0; t < c->tracks.size(); ++t)
+    if (cap > 0 && (!g_start_dev[t] || !g_len_dev[t])) return fail(MLX_ERR_INVALID, "null output row");
+  CK(cudaSetDevice(c->device));
+  return grain_segment_common(c, g_start_dev, g_len_dev, cap, counts_dev);
+}
+
+int mlx_grain_segment(mlx_ctx* c, int32_t* const* g_start, int32_t* const* g_len, int cap, int32_t* counts) {
+  if (!c || !g_start || !g_len || !counts || cap < 0) return fail(MLX_ERR_INVALID, "bad argument");
+  if (c->tracks.empty()) return fail(MLX_ERR_STATE, "no tracks uploaded");
+  const int nt = (int)c->tracks.size();
+  for (int t = 0; t < nt; ++t)
+    if (cap > 0 && (!g_start[t] || !g_len[t])) return fail(MLX_ERR_INVALID, "null output row");
+  CK(cudaSetDevice(c->device));
+  const size_t row = (size_t)std::max(cap, 1);
+  CK(c->seg_rows.reserve(sizeof(int32_t) * 2 * row * nt));
+  CK(c->seg_count.reserve(sizeof(int32_t) * nt));
+  int32_t* rows = static_cast<int32_t*>(c->seg_rows.p);
+  std::vector<int32_t*> ps(nt), pl(nt);
+  for (int t = 0; t < nt; ++t) {
+    ps[t] = rows + (size_t)(2 * t) * row;
+    pl[t] = rows + (size_t)(2 * t + 1) * row;
+  }
+  int rc = grain_segment_common(c, ps.data(), pl.data(), cap, static_cast<int32_t*>(c->seg_count.p));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(counts, c->seg_count.p, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int t = 0; t < nt; ++t) {
+    const int m = std::min(counts[t], cap);
+    if (m <= 0) continue;
+    CK(cudaMemcpyAsync(g_start[t], ps[t], sizeof(int32_t) * m, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(g_len[t], pl[t], sizeof(int32_t) * m, cudaMemcpyDeviceToHost, c->stream));
+  }
   CK(cudaStreamSynchronize(c->stream));
   return MLX_OK;
 }

@@ -11,6 +11,7 @@
 // bit-identical to the reference's scalar x86 arithmetic.
 #include <cuda_runtime.h>
 
+#include "grain_seg.cuh"
 #include "kernels.h"
 
 namespace mlx {
@@ -39,6 +40,140 @@ __global__ void __launch_bounds__(256) grain_kernel(const GrainArgs a) {
     if (a.out) a.out[o] = v;
     if (a.out_i16) a.out_i16[o] = (short)__double2int_rz((double)v * 32767.);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: grain segmentation (replaces the zero-crossing search of App::preproc, reference
+// app.cpp:156-235; bit logic and its derivation in grain_seg.cuh).
+//
+// K8a  grain_cross_kernel: the two crossing predicates for every sample of every track, data
+//      parallel.  A CTA covers 256 words (8192 samples): warps turn samples into sign words with
+//      __ballot_sync (one coalesced 128-byte load per word), the words meet in shared memory and
+//      every thread combines four of them into one word of Z7 and one of Z3.  HBM-bound: 4 bytes
+//      read and 1/4 byte written per sample.
+// K8b  grain_chain_kernel: the chain over grains is inherently serial (every grain starts where the
+//      previous one ended) but O(#grains): one CTA per track stages 32 KB slices of Z7 in shared
+//      memory (256 Ki samples, ~170 grains per refill) and warp 0 walks it -- 64 words around
+//      start + 1500, best probe per lane, __reduce_min_sync -- falling back to a forward scan of Z3
+//      in global memory when the window holds no crossing (app.cpp:194-231).
+constexpr int kSegWordsPerCta = 256;
+constexpr int kSegStageWords = 8192;
+
+__global__ void __launch_bounds__(256) grain_cross_kernel(const GrainSegTrack* __restrict__ tracks) {
+  __shared__ uint32_t sL[kSegWordsPerCta + 2], sR[kSegWordsPerCta + 2];
+  const GrainSegTrack tr = tracks[blockIdx.y];
+  const long long k0 = (long long)blockIdx.x * kSegWordsPerCta;  // first word of this CTA
+  if (k0 >= tr.nwords) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // sign words k0-1 .. k0+256 (one halo word each side); samples outside [0, n) never matter: the
+  // range test of seg_cross_word masks every position whose look-around leaves the track
+  for (int wi = warp; wi < kSegWordsPerCta + 2; wi += 8) {
+    const long long i = (k0 - 1 + wi) * 32 + lane;
+    const bool in = i >= 0 && i < tr.n;
+    const float v = in ? __ldg(tr.x + i) : 0.f;
+    const uint32_t l = __ballot_sync(0xffffffffu, in && !(v >= 0.f));
+    const uint32_t r = __ballot_sync(0xffffffffu, in && !(v < 0.f));
+    if (lane == 0) {
+      sL[wi] = l;
+      sR[wi] = r;
+    }
+  }
+  __syncthreads();
+  const long long k = k0 + threadIdx.x;
+  if (k < tr.nwords) {
+    const int w = threadIdx.x + 1;
+    tr.z7[k] = seg_cross_word(sL[w - 1], sL[w], sR[w], sR[w + 1], k, tr.n, 7);
+    tr.z3[k] = seg_cross_word(sL[w - 1], sL[w], sR[w], sR[w + 1], k, tr.n, 3);
+  }
+}
+
+__global__ void __launch_bounds__(256) grain_chain_kernel(const GrainSegTrack* __restrict__ tracks, int cap) {
+  __shared__ uint32_t stage[kSegStageWords];
+  __shared__ int s_start, s_count, s_done;
+  const GrainSegTrack tr = tracks[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int lim = (int)(tr.n - kGrainPreferred - 1);  // app.cpp:161
+  if (tid == 0) {
+    s_start = 0;
+    s_count = 0;
+    s_done = !(0 < lim);
+  }
+  __syncthreads();
+  while (!s_done) {
+    int start = s_start;
+    // refill: the staged slice begins at the word that holds the first probe of the next grain
+    const long long wbase = ((long long)start + kGrainPreferred - kGrainHalfSpan) >> 5;
+    for (int i = tid; i < kSegStageWords; i += 256) stage[i] = (wbase + i < tr.nwords) ? __ldg(tr.z7 + wbase + i) : 0u;
+    __syncthreads();
+    if (tid < 32) {
+      int count = s_count, done = 0;
+      while (true) {
+        if (!(start < lim)) {
+          done = 1;
+          break;
+        }
+        const int c = start + kGrainPreferred;
+        const long long w0 = (long long)(c - kGrainHalfSpan) >> 5;
+        if (w0 + kGrainWindowWords > wbase + kSegStageWords) break;  // window not staged: refill
+        uint32_t best = 0xffffffffu;
+#pragma unroll
+        for (int h = 0; h < kGrainWindowWords / 32; ++h) {
+          const long long wi = w0 + lane + 32 * h;
+          const uint32_t key = seg_word_key(stage[(int)(wi - wbase)], (int)(wi * 32), c);
+          best = key < best ? key : best;
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        int idx;
+        if (best != 0xffffffffu) {
+          idx = seg_key_index(best, c);
+        } else {
+          // no look-7 crossing within +-749: first look-3 crossing at or after start + 2250
+          const long long s = (long long)start + kGrainPreferred + kGrainPreferred / 2;
+          idx = -1;
+          for (long long kb = s >> 5; kb < tr.nwords; kb += 32) {
+            const long long kw = kb + lane;
+            uint32_t word = kw < tr.nwords ? __ldg(tr.z3 + kw) : 0u;
+            if (kw == (s >> 5)) word &= 0xffffffffu << (int)(s & 31);
+            const unsigned any = __ballot_sync(0xffffffffu, word != 0u);
+            if (any) {
+              const int src = __ffs((int)any) - 1;
+              const uint32_t wv = __shfl_sync(0xffffffffu, word, src);
+              idx = (int)((kb + src) * 32 + (__ffs((int)wv) - 1));
+              break;
+            }
+          }
+          if (idx < 0) {
+            done = 1;
+            break;
+          }
+        }
+        if (lane == 0 && count < cap) {
+          tr.g_start[count] = start;
+          tr.g_len[count] = idx - start;
+        }
+        ++count;
+        start = idx;
+      }
+      if (lane == 0) {
+        s_start = start;
+        s_count = count;
+        s_done = done;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *tr.count = s_count;
+}
+
+cudaError_t launch_grain_segment(const GrainSegTrack* tracks_dev, int ntracks, long long max_words, int cap,
+                                 cudaStream_t st) {
+  if (ntracks <= 0) return cudaSuccess;
+  if (max_words > 0) {
+    dim3 grid((unsigned)((max_words + kSegWordsPerCta - 1) / kSegWordsPerCta), ntracks);
+    grain_cross_kernel<<<grid, 256, 0, st>>>(tracks_dev);
+  }
+  grain_chain_kernel<<<ntracks, 256, 0, st>>>(tracks_dev, cap);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_grain(const GrainArgs& a, cudaStream_t st) {

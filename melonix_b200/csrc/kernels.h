@@ -107,4 +107,18 @@ struct GrainArgs {
 };
 cudaError_t launch_grain(const GrainArgs& a, cudaStream_t st);
 
+// ---- grain segmentation (K8)
+struct GrainSegTrack {
+  const float* x;      // sample 0 of the padded device copy
+  long long n;
+  long long nwords;    // words of z7 / z3: ceil(n / 32) + 1
+  uint32_t* z7;        // look-around-7 crossings, bit b of word k <-> idx = 32 k + b
+  uint32_t* z3;        // look-around-3 crossings
+  int* g_start;        // [cap]
+  int* g_len;          // [cap]
+  int* count;          // grains found (may exceed cap; only cap rows are written)
+};
+cudaError_t launch_grain_segment(const GrainSegTrack* tracks_dev, int ntracks, long long max_words, int cap,
+                                 cudaStream_t st);
+
 }  // namespace mlx

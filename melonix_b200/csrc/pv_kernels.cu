@@ -268,9 +268,12 @@ __device__ __forceinline__ float shift_one_bin_v2(const cplx<double>* zb, const 
   const uint32_t mb = __float_as_uint(mh.mag);
   // cut flip (sign bit of the stored magnitude): d' = d32 + 2^32 when d32 < 0, d32 - 2^32 otherwise
   const int hi_adj = ((int)mb >> 31) & (mh.d < 0 ? r_fix : -r_fix);
-  unsigned long long prod = c.base + (unsigned long long)((long long)mh.d * (long long)r_fix);
-  prod += (unsigned long long)(uint32_t)hi_adj << 32;
-  inc = (uint32_t)(prod >> 26);
+  // base + d * r_fix as ONE signed 32 x 32 + 64 multiply-add (the compiler expands the C expression
+  // into a 64 x 64 product), the flip term goes into the high word, the shift is a funnel shift
+  unsigned long long prod;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(prod) : "r"(mh.d), "r"(r_fix), "l"(c.base));
+  const uint32_t lo = (uint32_t)prod, hi = (uint32_t)(prod >> 32) + (uint32_t)hi_adj;
+  inc = __funnelshift_r(lo, hi, 26);
   return __uint_as_float(mb & 0x7fffffffu);
 }
 
@@ -429,11 +432,14 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     __syncthreads();
 
     // ---- pair phase: X[k], X[NC-k] from Z; phase advance against the previous frame
+    // frames of this batch that exist: gg in [g_lo, g_hi).  Frame -1 (only a = 0, bi = 0, gg = 0) has
+    // phi = 0 <=> X = 1, the initial value of "previous".
+    const int g_hi = (int)min((long long)G, b - f_first);
+    const int g_lo = f_first < 0 ? 1 : 0;
 #pragma unroll(kUnrollPair)
     for (int gg = 0; gg < G; ++gg) {
-      const long long ff = f_first + gg;
-      if (ff >= b) break;
-      if (ff < 0) continue;  // frame -1: phi = 0 <=> X = 1 (initial values)
+      if (gg >= g_hi) break;
+      if (gg < g_lo) continue;
       C* zb = buf + gg * BUF;
       const bool emit = (bi != 0 || gg != 0);  // the chunk's leading halo frame only seeds "previous"
 #pragma unroll
@@ -461,11 +467,14 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           pm[q] = xm;
         }
       }
-      if (tid == THREADS - 1) {  // DC and Nyquist are real: X[0] = Re Z0 + Im Z0, X[NC] = Re Z0 - Im Z0
+    }
+    if (tid == THREADS - 1) {  // DC and Nyquist are real: X[0] = Re Z0 + Im Z0, X[NC] = Re Z0 - Im Z0
+      for (int gg = g_lo; gg < g_hi; ++gg) {
+        C* zb = buf + gg * BUF;
         const C z0 = zb[0];
         const MagD m0 = analysis_real_bin(z0.x + z0.y, pp0, pm0);
         const MagD mn = analysis_real_bin(z0.x - z0.y, ppn, pmn);
-        if (emit) {
+        if (bi != 0 || gg != 0) {
           *reinterpret_cast<MagD*>(zb) = m0;
           *reinterpret_cast<MagD*>(zb + fft_pad(NC)) = mn;
         }
@@ -474,6 +483,34 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     __syncthreads();
 
     // ---- gather phase: bin shift, exact phase increment, chunk-local scan, spill to HBM
+#if MLX_GATHER_V2
+    if (fast_shift) {
+      // rows of frame gg: base pointer of the batch + compile-time offsets; g_cnt = frames before the
+      // end of the wave (their running phase is what the next wave starts from)
+      const int e_lo = bi == 0 ? 1 : 0;  // the chunk's leading halo frame emits nothing
+      const int g_cnt = (int)min((long long)g_hi, wv.we - f_first);
+      float* ps = sc.smag + (row0 + (size_t)(f_first - wv.wb)) * NBP + tid;
+      uint32_t* pl = sc.lacc + (row0 + (size_t)(f_first - wv.wb)) * NBP + tid;
+      const int r_fix = (int)wv.r_fix;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) {
+        if (gg >= e_lo && gg < g_hi) {
+          const C* zb = buf + gg * BUF;
+#pragma unroll
+          for (int q = 0; q < QB; ++q) {
+            if (tid + q * THREADS < NC) {
+              uint32_t inc;
+              const float smag = shift_one_bin_v2(zb, scq[q], r_fix, inc);
+              lacc[q] += inc;
+              if (gg == g_cnt - 1) totc[q] = lacc[q];
+              ps[gg * NBP + q * THREADS] = smag;
+              pl[gg * NBP + q * THREADS] = lacc[q];
+            }
+          }
+        }
+      }
+    } else
+#endif
 #pragma unroll(kUnrollGather)
     for (int gg = (bi == 0 ? 1 : 0); gg < G; ++gg) {
       const long long ff = f_first + gg;
@@ -492,20 +529,12 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         const int j = tid + q * THREADS;
         if (j < NC) {
           uint32_t kk, inc;
-          float smag;
-#if MLX_GATHER_V2
-          if (fast_shift) {
-            smag = shift_one_bin_v2(zb, scq[q], (int)r_fix, inc);
-          } else
-#endif
-          {
-            if (per_frame_rate) {
-              gather_entry_slow(j, r, NC, kk);
-            } else {
-              kk = gkq[q];
-            }
-            smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
+          if (per_frame_rate) {
+            gather_entry_slow(j, r, NC, kk);
+          } else {
+            kk = gkq[q];
           }
+          const float smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
           lacc[q] += inc;
           if (counted) totc[q] = lacc[q];
           sc.smag[row + j] = smag;
@@ -714,9 +743,16 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     }
   };
 
+  // chunks that end inside the track (all but the last one of a track) need no per-sample bounds test
+  const bool interior = b * H <= tr.n;
+  float* const pout = tr.out + a * H + 2 * tid;  // column 0 of this thread in hop a
+  const float* const psm = sc.smag + row0 * NBP;
+  const uint32_t* const pla = sc.lacc + row0 * NBP;
+
   for (int bi = 0; bi < nbatch; ++bi) {
     const int fb = bi * G;                       // frame index relative to a
     const int nfr = min(G, nfr_total - fb);      // frames present in this batch
+    float* const pob = pout + (long long)(fb - 3) * H;  // hop fb - 3: where frame fb's first quarter completes
 
     // ---- synthesis spectrum Y = smag e^{i theta}, folded for the N/2-point complex inverse.
     //      All global loads of a sub-batch are issued before the first use (latency hiding).
@@ -724,6 +760,31 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     for (int g0 = 0; g0 < nfr; g0 += GS) {
       float mk[GS][QP], mm[GS][QP], m0[GS], mn[GS];
       uint32_t ak[GS][QP], am[GS][QP], a0[GS], an[GS];
+      if (nfr == G) {  // full batch (all but the last of a chunk): rows at compile-time offsets
+        const float* msrc0 = psm + (size_t)(fb + g0) * NBP;
+        const uint32_t* asrc0 = pla + (size_t)(fb + g0) * NBP;
+#pragma unroll
+        for (int u = 0; u < GS; ++u) {
+          const float* msrc = msrc0 + u * NBP;
+          const uint32_t* asrc = asrc0 + u * NBP;
+#pragma unroll
+          for (int q = 0; q < QP; ++q) {
+            const int k = 1 + tid + q * THREADS;
+            if (k <= NC / 2) {
+              mk[u][q] = __ldg(msrc + k);
+              mm[u][q] = __ldg(msrc + NC - k);
+              ak[u][q] = __ldg(asrc + k);
+              am[u][q] = __ldg(asrc + NC - k);
+            }
+          }
+          if (tid == 0) {
+            m0[u] = __ldg(msrc);
+            mn[u] = __ldg(msrc + NC);
+            a0[u] = __ldg(asrc);
+            an[u] = __ldg(asrc + NC);
+          }
+        }
+      } else
 #pragma unroll
       for (int u = 0; u < GS; ++u) {
         const int gg = min(g0 + u, nfr - 1);  // clamp: duplicates of the last frame are never used
@@ -832,7 +893,12 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
             p0[c] = make_float2(p1[c].x + q1.x, p1[c].y + q1.y);
             p1[c] = make_float2(p2[c].x + q2.x, p2[c].y + q2.y);
             p2[c] = make_float2(q3.x, q3.y);
-            emit_hop(fb + gi - 3, i2, o);
+            if (interior) {
+              const int hrel = fb + gi - 3;
+              if (hrel >= 0 && hrel < nhop) *reinterpret_cast<float2*>(pob + gi * H + 2 * c * THREADS) = o;
+            } else {
+              emit_hop(fb + gi - 3, i2, o);
+            }
           }
         }
       }

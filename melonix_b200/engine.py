@@ -193,6 +193,29 @@ class Engine:
         self._lens = [size(t) for t in tracks]
 
     # ------------------------------------------------------------------ grain path
+    def grain_segment(self, cap: int | None = None):
+        """Zero-crossing grain segmentation of every uploaded track on the GPU (App::preproc,
+        reference app.cpp:156-235).  Returns [(g_start, g_len)] per track (int32 arrays)."""
+        nt = int(self._L.mlx_num_tracks(self._h))
+        lens = [int(self._L.mlx_track_len(self._h, t)) for t in range(nt)]
+        if cap is None:
+            cap = max(lens) // 751 + 1 if lens else 1
+        gs = np.zeros((nt, max(cap, 1)), np.int32)
+        gl = np.zeros((nt, max(cap, 1)), np.int32)
+        counts = np.zeros(nt, np.int32)
+        check(self._L.mlx_grain_segment(self._h, ptr_array([gs[t].ctypes.data for t in range(nt)]),
+                                        ptr_array([gl[t].ctypes.data for t in range(nt)]), cap, counts.ctypes.data))
+        self.last_grain_counts = counts
+        return [(gs[t, :min(int(counts[t]), cap)].copy(), gl[t, :min(int(counts[t]), cap)].copy()) for t in range(nt)]
+
+    def grain_segment_dev(self, g_start, g_len, counts, cap: int) -> None:
+        """g_start / g_len: int32 CUDA tensors [ntracks, cap]; counts: int32 CUDA tensor [ntracks]."""
+        nt = int(self._L.mlx_num_tracks(self._h))
+        assert g_start.is_cuda and g_len.is_cuda and counts.is_cuda and g_start.shape[0] == nt
+        check(self._L.mlx_grain_segment_dev(self._h, ptr_array([g_start[t].data_ptr() for t in range(nt)]),
+                                            ptr_array([g_len[t].data_ptr() for t in range(nt)]), cap,
+                                            counts.data_ptr()))
+
     def grain_render(self, track: int, g_start, g_len, g_rate, out_off, g_next, tail_zeros: int = 1500,
                      want_i16: bool = True):
         gs = np.ascontiguousarray(g_start, np.int32)

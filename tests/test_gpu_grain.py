@@ -106,3 +106,76 @@ def test_cpp_export_path(tmp_path, oracle):
     got = np.fromfile(tmp_path / "out.i16", np.int16)
     o = oracle.grain_export(x, 48000, [(10, 0, 0, 3.0), (x.size - 10, 0, 0, 3.0)])
     assert np.array_equal(got, o["pcm16"])
+
+
+# ------------------------------------------------------------------------------------------------
+# K8: grain segmentation on the device (App::preproc, reference app.cpp:156-235) -- integer-exact
+def _seg_cases():
+    fs = 48000
+    rng = np.random.default_rng(8)
+
+    def tone(f, sec, noise=0.0):
+        t = np.arange(int(sec * fs)) / fs
+        x = 0.4 * np.sin(2 * np.pi * f * t) + 0.2 * np.sin(2 * np.pi * 2.01 * f * t + 1.0)
+        return (x + noise * (rng.random(t.size) - 0.5)).astype(np.float32)
+
+    weird = tone(440, 5)
+    weird[::97] = -0.0           # -0.0 counts as ">= 0" (app.cpp:175)
+    weird[5::1013] = np.nan      # NaN passes both sign tests
+    return {
+        "two_tone": S.two_tone(20.0),
+        "vibrato": S.vibrato_tone(30.0, seed=4),
+        "noisy": tone(220, 20, 0.05),
+        "sparse_33Hz": tone(33, 20),
+        "fallback_9Hz": tone(9, 30),               # no look-7 crossing within +-749: forward look-3 scan
+        "fallback_9Hz_noisy": tone(9, 30, 0.02),
+        "white": tone(0, 10, 1.0),
+        "silence": np.zeros(100000, np.float32),
+        "negative_dc": np.full(100000, -0.25, np.float32),
+        "clip_1400": tone(220, 1400 / fs),          # shorter than one grain: the loop never runs (app.cpp:161)
+        "clip_1502": tone(220, 1502 / fs),
+        "clip_3100": tone(220, 3100 / fs),
+        "empty": np.zeros(0, np.float32),
+        "neg_zero_and_nan": weird,
+        "long": S.vibrato_tone(200.0, seed=5),      # several 256 Ki-sample stage refills per chain
+    }
+
+
+def test_grain_segmentation_matches_reference_restatement(engine, oracle):
+    from melonix_b200 import hostlib as H
+    cases = _seg_cases()
+    names = list(cases)
+    engine.upload_tracks([cases[k] for k in names])      # all tracks segmented by ONE call
+    got = engine.grain_segment()
+    for name, (gs, gl) in zip(names, got):
+        os_, ol = oracle.grain_segment(cases[name])
+        assert gs.size == os_.size, name
+        assert np.array_equal(gs, os_) and np.array_equal(gl, ol), name
+        hs, hl = H.grain_segment(cases[name])              # host C++ mirror
+        assert np.array_equal(gs, hs) and np.array_equal(gl, hl), name
+    counts = dict(zip(names, (g[0].size for g in got)))
+    assert counts["two_tone"] == 628                      # KAT-4 probe of SURVEY.md section 4
+    assert counts["silence"] == counts["negative_dc"] == counts["clip_1400"] == counts["empty"] == 0
+    assert counts["fallback_9Hz"] > 0 and counts["long"] > 6000
+
+
+def test_grain_segmentation_cap_and_device_entry(engine, oracle):
+    import torch
+    x = S.two_tone(20.0)
+    engine.upload_tracks([x, x[:200000]])
+    os_, ol = oracle.grain_segment(x)
+    got = engine.grain_segment(cap=100)                     # too small: rows truncated, counts complete
+    assert got[0][0].size == 100 and int(engine.last_grain_counts[0]) == os_.size
+    assert np.array_equal(got[0][0], os_[:100]) and np.array_equal(got[0][1], ol[:100])
+    engine.use_torch_stream()
+    cap = x.size // 751 + 1
+    gs = torch.zeros((2, cap), dtype=torch.int32, device="cuda")
+    gl = torch.zeros((2, cap), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+    engine.grain_segment_dev(gs, gl, cnt, cap)
+    torch.cuda.synchronize()
+    c = cnt.cpu().numpy()
+    assert c[0] == os_.size
+    assert np.array_equal(gs[0, :c[0]].cpu().numpy(), os_) and np.array_equal(gl[0, :c[0]].cpu().numpy(), ol)
+    o2s, o2l = oracle.grain_segment(x[:200000])
+    assert c[1] == o2s.size and np.array_equal(gs[1, :c[1]].cpu().numpy(), o2s)

@@ -48,6 +48,19 @@ def test_spec_frame_steps_emulated_on_host(tmp_path):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
 
 
+def test_grain_segmentation_bit_logic_emulated_on_host(tmp_path):
+    """Bit logic of the device grain segmentation (grain_seg.cuh) run sequentially against the oracle
+    restatement of App::preproc (app.cpp:156-235)."""
+    exe = tmp_path / "grain_seg_emul"
+    gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    o = tmp_path / "grain_ref.o"
+    subprocess.run(["gcc", "-O2", "-c", str(ROOT / "oracle/grain_ref.c"), "-o", str(o)], check=True, capture_output=True)
+    subprocess.run([gxx, "-std=c++17", "-O2", str(ROOT / "tests/host/grain_seg_emul.cpp"), str(o), "-o", str(exe), "-lm"],
+                   check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
+
+
 def test_c_abi_exports_every_declared_symbol():
     from melonix_b200 import capi, hostlib
     L = capi.lib()
