@@ -28,7 +28,7 @@
 #include "tma.cuh"
 
 #ifndef MLX_UNROLL_PAIR
-#define MLX_UNROLL_PAIR 2
+#define MLX_UNROLL_PAIR 4
 #endif
 #ifndef MLX_UNROLL_GATHER
 #define MLX_UNROLL_GATHER 2
@@ -36,8 +36,12 @@
 #ifndef MLX_GATHER_V2
 #define MLX_GATHER_V2 1  // constant-rate bin shift with frame-invariant constants (bit-identical to v1)
 #endif
+#ifndef MLX_KA_CTAS_MAXN
+#define MLX_KA_CTAS_MAXN 2048  // largest fftN analysed with MLX_KA_CTAS CTAs per SM (beyond: one 512-thread CTA)
+#endif
 #ifndef MLX_KA_CTAS
-#define MLX_KA_CTAS 1  // analysis CTAs per SM: 1 x 512 threads or 2 x 256 threads (same frames in flight)
+#define MLX_KA_CTAS 2  // analysis CTAs per SM for small fftN: 2 x 256 threads (measured 5 % faster than 1 x 512:
+                       // the FP64 FFT phase of one CTA overlaps the integer/FP32 phases of the other)
 #endif
 
 namespace mlx {
@@ -66,11 +70,13 @@ struct PvCfg {
 };
 
 // Frames per batch: synthesis keeps G*(N/2) = 4096 complex points in flight (256 threads, 2 CTAs per
-// SM), analysis 8192 (512 threads, one CTA per SM): 16 resident warps per SM in both kernels.
+// SM); analysis the same for fftN <= MLX_KA_CTAS_MAXN and 8192 points in one 512-thread CTA per SM
+// beyond (the per-thread bin state of a 256-thread CTA spills there): 16 resident warps per SM.
 template <int N>
 struct PvG {
   static constexpr int value = 8192 / N;    // K_S
-  static constexpr int analyze = (16384 / MLX_KA_CTAS) / N; // K_A
+  static constexpr int ka_ctas = (N <= MLX_KA_CTAS_MAXN) ? MLX_KA_CTAS : 1;  // (two 8192-point CTAs do not fit one SM)
+  static constexpr int analyze = (16384 / ka_ctas) / N;           // K_A
 };
 
 // what the pair phase leaves for the gather phase, stored in the first 8 bytes of the bin's (dead)
@@ -305,7 +311,7 @@ __device__ __forceinline__ void sincos_turns(uint32_t acc, float& s, float& c) {
 // ------------------------------------------------------------------------------------------------
 // K_A
 template <int N, int G>
-__global__ void __launch_bounds__(PvCfg<N, G>::THREADS, MLX_KA_CTAS)
+__global__ void __launch_bounds__(PvCfg<N, G>::THREADS, PvG<N>::ka_ctas)
 pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = PvCfg<N, G>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NB = Cfg::NB, NBP = Cfg::NBP;
@@ -949,7 +955,16 @@ cudaError_t pv_configure(int fftN) {
   return cudaSuccess;
 }
 int pv_group_count(int fftN) { return 8192 / fftN; }
-int pv_group_count_analyze(int fftN) { return (16384 / MLX_KA_CTAS) / fftN; }
+int pv_group_count_analyze(int fftN) {
+  switch (fftN) {
+    case 512: return PvG<512>::analyze;
+    case 1024: return PvG<1024>::analyze;
+    case 2048: return PvG<2048>::analyze;
+    case 4096: return PvG<4096>::analyze;
+    case 8192: return PvG<8192>::analyze;
+  }
+  return 1;
+}
 int pv_threads(int) { return 256; }
 size_t pv_analyze_smem(int fftN) {
   switch (fftN) {
