@@ -36,6 +36,12 @@
 #ifndef MLX_GATHER_V2
 #define MLX_GATHER_V2 1  // constant-rate bin shift with frame-invariant constants (bit-identical to v1)
 #endif
+#ifndef MLX_KS_MINB
+#define MLX_KS_MINB 2      // synthesis CTAs per SM the register allocation is bounded for
+#endif
+#ifndef MLX_KS_WIN_SMEM
+#define MLX_KS_WIN_SMEM 0  // synthesis window in shared memory instead of 32 registers per thread
+#endif
 #ifndef MLX_KA_CTAS_MAXN
 #define MLX_KA_CTAS_MAXN 2048  // largest fftN analysed with MLX_KA_CTAS CTAs per SM (beyond: one 512-thread CTA)
 #endif
@@ -66,7 +72,7 @@ struct PvCfg {
   static constexpr int BUFS = BUF + 2;  // + the Nyquist bin's (mag, d) record + an all-zero record (empty K_j)
   static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUFS + (WIN_D ? sizeof(double) * N : 0) +
                                    sizeof(float) * 2 * TILE + 64;
-  static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + 64;
+  static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + (MLX_KS_WIN_SMEM ? sizeof(float) * N : 0) + 64;
 };
 
 // Frames per batch: synthesis keeps G*(N/2) = 4096 complex points in flight (256 threads, 2 CTAs per
@@ -700,7 +706,7 @@ pv_scan_kernel(int nb, int nbp, int nchunks, const PvScratch sc) {
 // ------------------------------------------------------------------------------------------------
 // K_S
 template <int N, int G>
-__global__ void __launch_bounds__(PvCfg<N, G>::THREADS, 2)
+__global__ void __launch_bounds__(PvCfg<N, G>::THREADS, MLX_KS_MINB)
 pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = PvCfg<N, G>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NBP = Cfg::NBP;
@@ -726,6 +732,11 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
 
   FftTwiddles<float, NC, +1> twd;
   twd.init(t, tb.tw_f);
+#if MLX_KS_WIN_SMEM
+  float* s_wsyn = reinterpret_cast<float*>(buf + G * BUF);  // [N]
+  for (int i = tid; i < N; i += THREADS) s_wsyn[i] = tb.wsyn[i];
+  __syncthreads();
+#else
   float wreg[32];
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
@@ -733,6 +744,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     wreg[2 * m] = w2.x;
     wreg[2 * m + 1] = w2.y;
   }
+#endif
   C wr[QP];
   uint32_t prek[QP], prem[QP];
 #pragma unroll
@@ -889,8 +901,14 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
       F::run(x, zb, t, twd, bar);
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
+#if MLX_KS_WIN_SMEM
+        const float2 w2 = *reinterpret_cast<const float2*>(s_wsyn + 2 * (t + m * TPF));
+        x[m].x *= w2.x;
+        x[m].y *= w2.y;
+#else
         x[m].x *= wreg[2 * m];
         x[m].y *= wreg[2 * m + 1];
+#endif
       }
       F::store(x, zb, t);
     }
