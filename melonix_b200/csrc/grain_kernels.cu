@@ -47,10 +47,10 @@ __global__ void __launch_bounds__(256) grain_kernel(const GrainArgs a) {
 // app.cpp:156-235; bit logic and its derivation in grain_seg.cuh).
 //
 // K8a  grain_cross_kernel: the two crossing predicates for every sample of every track, data
-//      parallel.  A CTA covers 256 words (8192 samples): warps turn samples into sign words with
-//      __ballot_sync (one coalesced 128-byte load per word), the words meet in shared memory and
-//      every thread combines four of them into one word of Z7 and one of Z3.  HBM-bound: 4 bytes
-//      read and 1/4 byte written per sample.
+//      parallel.  A CTA covers 256 words (8192 samples): warps turn samples into sign words (one
+//      coalesced float4 load per lane, four sign bits per lane OR-reduced over octets of lanes), the
+//      words meet in shared memory and every thread combines four of them into one word of Z7 and one
+//      of Z3.  HBM-bound: 4 bytes read and 1/4 byte written per sample.
 // K8b  grain_chain_kernel: the chain over grains is inherently serial (every grain starts where the
 //      previous one ended) but O(#grains): one CTA per track stages 32 KB slices of Z7 in shared
 //      memory (256 Ki samples, ~170 grains per refill) and warp 0 walks it -- 64 words around
@@ -60,28 +60,40 @@ constexpr int kSegWordsPerCta = 256;
 constexpr int kSegStageWords = 8192;
 
 __global__ void __launch_bounds__(256) grain_cross_kernel(const GrainSegTrack* __restrict__ tracks) {
-  __shared__ uint32_t sL[kSegWordsPerCta + 2], sR[kSegWordsPerCta + 2];
+  // sign words k0-4 .. k0+259 (the CTA's 256 words plus one 128-sample group on each side)
+  __shared__ uint32_t sL[kSegWordsPerCta + 8], sR[kSegWordsPerCta + 8];
   const GrainSegTrack tr = tracks[blockIdx.y];
   const long long k0 = (long long)blockIdx.x * kSegWordsPerCta;  // first word of this CTA
   if (k0 >= tr.nwords) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // sign words k0-1 .. k0+256 (one halo word each side); samples outside [0, n) never matter: the
-  // range test of seg_cross_word masks every position whose look-around leaves the track
-  for (int wi = warp; wi < kSegWordsPerCta + 2; wi += 8) {
-    const long long i = (k0 - 1 + wi) * 32 + lane;
-    const bool in = i >= 0 && i < tr.n;
-    const float v = in ? __ldg(tr.x + i) : 0.f;
-    const uint32_t l = __ballot_sync(0xffffffffu, in && !(v >= 0.f));
-    const uint32_t r = __ballot_sync(0xffffffffu, in && !(v < 0.f));
-    if (lane == 0) {
-      sL[wi] = l;
-      sR[wi] = r;
+  // One warp iteration = 128 samples as one float4 per lane (a coalesced 512-byte load); the lane's
+  // four sign bits are shifted to their place inside the word of its octet and OR-reduced over the
+  // octet (three butterfly shuffles).  Samples outside [0, n) are read from the zero padding kept around every track and
+  // never matter: the range test of seg_cross_word masks every position whose look-around leaves the
+  // track.
+  for (int grp = warp; grp < kSegWordsPerCta / 4 + 2; grp += 8) {
+    const long long i = (k0 - 4 + 4 * grp) * 32 + 4 * lane;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(tr.x + i));
+    const uint32_t l = (!(v.x >= 0.f) ? 1u : 0u) | (!(v.y >= 0.f) ? 2u : 0u) | (!(v.z >= 0.f) ? 4u : 0u) |
+                       (!(v.w >= 0.f) ? 8u : 0u);
+    const uint32_t r = (!(v.x < 0.f) ? 1u : 0u) | (!(v.y < 0.f) ? 2u : 0u) | (!(v.z < 0.f) ? 4u : 0u) |
+                       (!(v.w < 0.f) ? 8u : 0u);
+    const int sh = 4 * (lane & 7);
+    uint32_t lw = l << sh, rw = r << sh;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {  // OR over the octet of lanes that shares a word
+      lw |= __shfl_xor_sync(0xffffffffu, lw, o);
+      rw |= __shfl_xor_sync(0xffffffffu, rw, o);
+    }
+    if ((lane & 7) == 0) {
+      sL[4 * grp + (lane >> 3)] = lw;
+      sR[4 * grp + (lane >> 3)] = rw;
     }
   }
   __syncthreads();
   const long long k = k0 + threadIdx.x;
   if (k < tr.nwords) {
-    const int w = threadIdx.x + 1;
+    const int w = threadIdx.x + 4;
     tr.z7[k] = seg_cross_word(sL[w - 1], sL[w], sR[w], sR[w + 1], k, tr.n, 7);
     tr.z3[k] = seg_cross_word(sL[w - 1], sL[w], sR[w], sR[w + 1], k, tr.n, 3);
   }

@@ -179,3 +179,12 @@ def test_grain_segmentation_cap_and_device_entry(engine, oracle):
     assert np.array_equal(gs[0, :c[0]].cpu().numpy(), os_) and np.array_equal(gl[0, :c[0]].cpu().numpy(), ol)
     o2s, o2l = oracle.grain_segment(x[:200000])
     assert c[1] == o2s.size and np.array_equal(gs[1, :c[1]].cpu().numpy(), o2s)
+
+
+def test_grain_segmentation_golden(engine):
+    """Committed fixture (tests/golden/grain_p3.npz, made by tests/golden/make_golden.py from the oracle)."""
+    g = np.load(GOLD / "grain_p3.npz")
+    x = S.two_tone(float(g["seconds"]))
+    engine.upload_tracks([x])
+    gs, gl = engine.grain_segment()[0]
+    assert np.array_equal(gs, g["g_start"]) and np.array_equal(gl, g["g_len"])
