@@ -53,9 +53,10 @@ __global__ void __launch_bounds__(256) grain_kernel(const GrainArgs a) {
 //      of Z3.  HBM-bound: 4 bytes read and 1/4 byte written per sample.
 // K8b  grain_chain_kernel: the chain over grains is inherently serial (every grain starts where the
 //      previous one ended) but O(#grains): one CTA per track stages 32 KB slices of Z7 in shared
-//      memory (256 Ki samples, ~170 grains per refill) and warp 0 walks it -- 64 words around
-//      start + 1500, best probe per lane, __reduce_min_sync -- falling back to a forward scan of Z3
-//      in global memory when the window holds no crossing (app.cpp:194-231).
+//      memory (256 Ki samples, ~170 grains per refill) and warp 0 walks it -- 24 lanes x 64 bits
+//      around start + 1500, two ballots find the nearest crossing on either side of the centre --
+//      falling back to a forward scan of Z3 in global memory when the window holds no crossing
+//      (app.cpp:194-231).
 constexpr int kSegWordsPerCta = 256;
 constexpr int kSegStageWords = 8192;
 
@@ -124,20 +125,25 @@ __global__ void __launch_bounds__(256) grain_chain_kernel(const GrainSegTrack* _
           done = 1;
           break;
         }
-        const int c = start + kGrainPreferred;
-        const long long w0 = (long long)(c - kGrainHalfSpan) >> 5;
+        const int lo = start + kGrainPreferred - kGrainHalfSpan;  // first probe position
+        const int sbit = lo & 31;
+        const long long w0 = (long long)lo >> 5;
         if (w0 + kGrainWindowWords > wbase + kSegStageWords) break;  // window not staged: refill
-        uint32_t best = 0xffffffffu;
-#pragma unroll
-        for (int h = 0; h < kGrainWindowWords / 32; ++h) {
-          const long long wi = w0 + lane + 32 * h;
-          const uint32_t key = seg_word_key(stage[(int)(wi - wbase)], (int)(wi * 32), c);
-          best = key < best ? key : best;
-        }
-        best = __reduce_min_sync(0xffffffffu, best);
+        // lane l < 24 owns bits [64 l, 64 l + 64) from bit 0 of word w0 (grain_seg.cuh)
+        const int wi = (int)(w0 - wbase) + 2 * lane;
+        const unsigned long long bits =
+            lane < 24 ? ((unsigned long long)stage[wi] | ((unsigned long long)stage[wi + 1] << 32)) : 0ull;
+        const SegSplit sp = seg_lane_split(bits, lane, sbit);
+        const unsigned b_ge = __ballot_sync(0xffffffffu, sp.ge != 0ull);
+        const unsigned b_lt = __ballot_sync(0xffffffffu, sp.lt != 0ull);
+        const int lane_ge = b_ge ? __ffs((int)b_ge) - 1 : -1;
+        const int lane_lt = b_lt ? 31 - __clz((int)b_lt) : -1;
+        const unsigned long long w_ge = __shfl_sync(0xffffffffu, sp.ge, lane_ge & 31);
+        const unsigned long long w_lt = __shfl_sync(0xffffffffu, sp.lt, lane_lt & 31);
+        const int rel = seg_pick(lane_ge, w_ge, lane_lt, w_lt, sbit);
         int idx;
-        if (best != 0xffffffffu) {
-          idx = seg_key_index(best, c);
+        if (rel >= 0) {
+          idx = (int)(w0 * 32) + rel;
         } else {
           // no look-7 crossing within +-749: first look-3 crossing at or after start + 2250
           const long long s = (long long)start + kGrainPreferred + kGrainPreferred / 2;

@@ -75,6 +75,55 @@ MLX_HD uint32_t seg_word_key(uint32_t word, int p0, int c) {
   return key;
 }
 
+// ---- warp-cooperative form of the same search (used by the chain kernel) -----------------------
+// The 1499-sample window [lo, hi] = [c - 749, c + 749] starts at bit s = lo & 31 of word w0 = lo >> 5.
+// Lane l (0..23) owns the 64 bits [64 l, 64 l + 64) relative to bit 0 of word w0: two staged words.
+// seg_lane_split() masks the lane's bits to the window and splits them at the centre c (relative
+// position s + 749): `ge` = probes at or after c, `lt` = probes before c.  The nearest probe on each
+// side is then the lowest set bit of the lowest lane with ge != 0 and the highest set bit of the
+// highest lane with lt != 0 (two ballots on the device); seg_pick() applies the reference's order
+// (+d is probed before -d, app.cpp:166) and returns the position relative to bit 0 of word w0, or -1.
+struct SegSplit {
+  unsigned long long ge, lt;
+};
+MLX_HD SegSplit seg_lane_split(unsigned long long bits, int lane, int s) {
+  const int first = 64 * lane;                       // relative position of the lane's bit 0
+  const int last_rel = s + 2 * kGrainHalfSpan;       // relative position of hi
+  const int c_rel = s + kGrainHalfSpan;              // relative position of c
+  unsigned long long m = bits;
+  if (lane == 0) m &= ~0ull << s;                    // below lo (s < 32: only lane 0 is cut)
+  if (first > last_rel) m = 0ull;                    // lanes past hi
+  else if (first + 63 > last_rel) m &= ~0ull >> (63 - (last_rel - first));
+  unsigned long long gem;                            // bits at or after c
+  if (first >= c_rel) gem = ~0ull;
+  else if (first + 63 < c_rel) gem = 0ull;
+  else gem = ~0ull << (c_rel - first);
+  return SegSplit{m & gem, m & ~gem};
+}
+MLX_HD int seg_ctz64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
+MLX_HD int seg_clz64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  return __clzll((long long)v);
+#else
+  return __builtin_clzll(v);
+#endif
+}
+// lane_ge / lane_lt: lowest lane with ge != 0 / highest lane with lt != 0 (or -1); w_ge / w_lt: their words
+MLX_HD int seg_pick(int lane_ge, unsigned long long w_ge, int lane_lt, unsigned long long w_lt, int s) {
+  const int c_rel = s + kGrainHalfSpan;
+  const int p_ge = lane_ge >= 0 ? 64 * lane_ge + seg_ctz64(w_ge) : -1;
+  const int p_lt = lane_lt >= 0 ? 64 * lane_lt + 63 - seg_clz64(w_lt) : -1;
+  if (p_ge < 0) return p_lt;
+  if (p_lt < 0) return p_ge;
+  return (p_ge - c_rel <= c_rel - p_lt) ? p_ge : p_lt;
+}
+
 // index the key stands for
 MLX_HD int seg_key_index(uint32_t key, int c) {
   const int d = (int)(key >> 1);

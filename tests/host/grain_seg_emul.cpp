@@ -15,7 +15,7 @@ using namespace mlx;
 static int run_case(const char* name, const std::vector<float>& w) {
   const long long n = (long long)w.size();
   const long long nwords = (n + 31) / 32 + 1;
-  std::vector<uint32_t> L(nwords + 2, 0u), R(nwords + 2, 0u), z7(nwords + kGrainWindowWords + 2, 0u),
+  std::vector<uint32_t> L(nwords + 2, 0u), R(nwords + 2, 0u), z7(nwords + kGrainWindowWords + 8, 0u),
       z3(nwords + kGrainWindowWords + 2, 0u);
   auto Lw = [&](long long k) { return (k < 0 || k >= nwords) ? 0u : L[k]; };
   auto Rw = [&](long long k) { return (k < 0 || k >= nwords) ? 0u : R[k]; };
@@ -55,9 +55,41 @@ static int run_case(const char* name, const std::vector<float>& w) {
     gl.push_back(idx - start);
     start = idx;
   }
+  // the same chain with the warp-cooperative helpers (lanes emulated one after the other)
+  std::vector<int> gs2, gl2;
+  start = 0;
+  while (start < lim) {
+    const int c = start + kGrainPreferred, lo = c - kGrainHalfSpan;
+    const int sbit = lo & 31, w0 = lo >> 5;
+    int lane_ge = -1, lane_lt = -1;
+    unsigned long long w_ge = 0, w_lt = 0;
+    for (int lane = 0; lane < 32; ++lane) {
+      const unsigned long long bits = (unsigned long long)z7[w0 + 2 * lane] | ((unsigned long long)z7[w0 + 2 * lane + 1] << 32);
+      const SegSplit sp = seg_lane_split(lane < 24 ? bits : 0xdeadbeefdeadbeefull, lane, sbit);
+      if (sp.ge && lane_ge < 0) { lane_ge = lane; w_ge = sp.ge; }
+      if (sp.lt) { lane_lt = lane; w_lt = sp.lt; }
+    }
+    const int rel = seg_pick(lane_ge, w_ge, lane_lt, w_lt, sbit);
+    int idx = -1;
+    if (rel >= 0) {
+      idx = w0 * 32 + rel;
+    } else {
+      const long long s0 = (long long)start + kGrainPreferred + kGrainPreferred / 2;
+      for (long long k = s0 >> 5; k < nwords && idx < 0; ++k) {
+        uint32_t word = z3[k];
+        if (k == (s0 >> 5)) word &= 0xffffffffu << (int)(s0 & 31);
+        if (word) idx = (int)(k * 32 + __builtin_ctz(word));
+      }
+      if (idx < 0) break;
+    }
+    gs2.push_back(start);
+    gl2.push_back(idx - start);
+    start = idx;
+  }
+  int bad2 = gs2 != gs || gl2 != gl;
   std::vector<int32_t> os(n / 700 + 8), ol(n / 700 + 8);
   const int cnt = mlxo_grain_segment(w.data(), n, os.data(), ol.data(), (int)os.size());
-  int bad = (cnt != (int)gs.size());
+  int bad = (cnt != (int)gs.size()) || bad2;
   for (int i = 0; i < cnt && i < (int)gs.size() && !bad; ++i) bad = (os[i] != gs[i]) || (ol[i] != gl[i]);
   std::printf("%-28s n=%8lld grains oracle %6d emul %6zu %s\n", name, n, cnt, gs.size(), bad ? "MISMATCH" : "ok");
   return bad;
