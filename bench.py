@@ -246,6 +246,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and os.environ.get("MLX_BENCH_NUMA", "1") != "0":
+        from melonix_b200.dist import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local)  # pinned e2e buffers local to the GPU's PCIe root
 
     def barrier():
         if world > 1:
@@ -364,7 +368,7 @@ def main():
                                 tracks_per_gpu=nt, seconds_per_track=args.seconds, fft=FFT_N, hop=HOP,
                                 semitones=SEMITONES, sample_rate=FS, frames_per_gpu=frames_per_rank,
                                 analysis_fft="f64", synthesis_fft="f32", phase_accumulator="u32",
-                                wave_mib=args.wave_mib,
+                                wave_mib=args.wave_mib, numa_binding=numa,
                                 l2="inputs and outputs (3.7 GB each per GPU) exceed the 126 MB L2; no flush needed"),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)

@@ -155,6 +155,16 @@ MLX_HD void dft_r(cplx<T> (&v)[R]) {
   else dft16<DIR>(v);
 }
 
+// p[r-1] = w^r, r = 1..15, by a product tree of depth <= 4 (keeps the float twiddle error at a few ulp)
+template <typename T>
+MLX_HD void power_tree16(cplx<T> (&p)[15], const cplx<T> w) {
+  const cplx<T> w2 = cmul(w, w), w3 = cmul(w2, w), w4 = cmul(w2, w2);
+  const cplx<T> w5 = cmul(w4, w), w6 = cmul(w4, w2), w7 = cmul(w4, w3), w8 = cmul(w4, w4);
+  p[0] = w; p[1] = w2; p[2] = w3; p[3] = w4; p[4] = w5; p[5] = w6; p[6] = w7; p[7] = w8;
+  p[8] = cmul(w8, w); p[9] = cmul(w8, w2); p[10] = cmul(w8, w3); p[11] = cmul(w8, w4);
+  p[12] = cmul(w8, w5); p[13] = cmul(w8, w6); p[14] = cmul(w8, w7);
+}
+
 // v[r] *= w^r, r = 1..R-1
 template <int R, typename T>
 MLX_HD void twiddle_powers(cplx<T> (&v)[R], const cplx<T> w) {
@@ -173,8 +183,13 @@ MLX_HD void twiddle_powers(cplx<T> (&v)[R], const cplx<T> w) {
       v[r] = cmul(v[r], p);
       if (r + 1 < R) p = cmul(p, w);
     }
+  } else if constexpr (R == 16) {
+    cplx<T> p[15];
+    power_tree16(p, w);
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], p[r - 1]);
   } else {
-    // float: product tree of depth <= 4 keeps the twiddle error at a few ulp
+    // float, radix 8: the first half of the same tree
     const cplx<T> w2 = cmul(w, w), w3 = cmul(w2, w), w4 = cmul(w2, w2);
     const cplx<T> w5 = cmul(w4, w), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
     v[1] = cmul(v[1], w);
@@ -184,17 +199,6 @@ MLX_HD void twiddle_powers(cplx<T> (&v)[R], const cplx<T> w) {
     v[5] = cmul(v[5], w5);
     v[6] = cmul(v[6], w6);
     v[7] = cmul(v[7], w7);
-    if constexpr (R == 16) {
-      const cplx<T> w8 = cmul(w4, w4);
-      v[8] = cmul(v[8], w8);
-      v[9] = cmul(v[9], cmul(w8, w));
-      v[10] = cmul(v[10], cmul(w8, w2));
-      v[11] = cmul(v[11], cmul(w8, w3));
-      v[12] = cmul(v[12], cmul(w8, w4));
-      v[13] = cmul(v[13], cmul(w8, w5));
-      v[14] = cmul(v[14], cmul(w8, w6));
-      v[15] = cmul(v[15], cmul(w8, w7));
-    }
   }
 }
 
@@ -231,10 +235,15 @@ struct FftPlan {
 
 // Per-thread twiddles (constant across frames): w[woff(s) + b] = exp(DIR*2*pi*i*k/(NS*R)),
 // k = (t + b*TPF) mod NS.  `table[m] = exp(-2*pi*i*m/NC)` (forward), m in [0, NC).
-template <typename T, int NC, int DIR>
+// PRE1: also keep the 15 powers of the stage-1 twiddle (radix-16 second stage, one butterfly per
+// thread) in registers instead of rebuilding them per transform -- the same product tree, so the
+// results are bit-identical; costs 30 registers, saves 14 complex products per transform.
+template <typename T, int NC, int DIR, bool PRE1 = false>
 struct FftTwiddles {
   using P = FftPlan<NC>;
+  static constexpr bool kPre1 = PRE1 && P::NSTAGES >= 2 && P::radix(1) == 16 && sizeof(T) == 4;
   cplx<T> w[P::NW];
+  cplx<T> p1[kPre1 ? 15 : 1];
   MLX_HD void init(int t, const cplx<T>* table) {
 #pragma unroll
     for (int s = 1; s < P::NSTAGES; ++s) {
@@ -247,6 +256,12 @@ struct FftTwiddles {
         if (DIR > 0) v.y = -v.y;
         w[P::woff(s) + b] = v;
       }
+    }
+    if constexpr (kPre1) {
+      cplx<T> p[15];
+      power_tree16(p, w[P::woff(1)]);
+#pragma unroll
+      for (int r = 0; r < 15; ++r) p1[r] = p[r];
     }
   }
 };
@@ -278,8 +293,8 @@ struct Fft {
 
   // butterflies of stage S on the register slots; non-last stages scatter to buf, the last stage
   // leaves natural-order results in the slots.
-  template <int S>
-  static MLX_HD void compute(C (&x)[16], C* buf, int t, const FftTwiddles<T, NC, DIR>& tw) {
+  template <int S, class TW>
+  static MLX_HD void compute(C (&x)[16], C* buf, int t, const TW& tw) {
     constexpr int R = P::radix(S), NS = P::ns(S), BPT = 16 / R;
     constexpr bool LAST = (S == P::NSTAGES - 1);
 #pragma unroll
@@ -287,7 +302,12 @@ struct Fft {
       C v[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = x[b + r * BPT];
-      if constexpr (S > 0) twiddle_powers<R>(v, tw.w[P::woff(S) + b]);
+      if constexpr (S == 1 && TW::kPre1) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw.p1[r - 1]);
+      } else if constexpr (S > 0) {
+        twiddle_powers<R>(v, tw.w[P::woff(S) + b]);
+      }
       dft_r<R, DIR>(v);
       if constexpr (LAST) {
 #pragma unroll
@@ -310,9 +330,8 @@ struct Fft {
 #ifdef __CUDACC__
   // Full transform for one thread of the group.  in: x[m] = in[t + m*TPF]; out: x[m] = out[t + m*TPF].
   // `buf` must not be in use by the group when run() is entered.  Bar::sync() synchronises the group.
-  template <int S, class Bar>
-  static __device__ __forceinline__ void run_from(C (&x)[16], C* buf, int t,
-                                                  const FftTwiddles<T, NC, DIR>& tw, Bar& bar) {
+  template <int S, class TW, class Bar>
+  static __device__ __forceinline__ void run_from(C (&x)[16], C* buf, int t, const TW& tw, Bar& bar) {
     if constexpr (S < P::NSTAGES) {
       if constexpr (S > 0) {
         bar.sync();  // stage S-1 stores visible
@@ -323,9 +342,8 @@ struct Fft {
       run_from<S + 1>(x, buf, t, tw, bar);
     }
   }
-  template <class Bar>
-  static __device__ __forceinline__ void run(C (&x)[16], C* buf, int t,
-                                             const FftTwiddles<T, NC, DIR>& tw, Bar& bar) {
+  template <class TW, class Bar>
+  static __device__ __forceinline__ void run(C (&x)[16], C* buf, int t, const TW& tw, Bar& bar) {
     run_from<0>(x, buf, t, tw, bar);
   }
 #endif

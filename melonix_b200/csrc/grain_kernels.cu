@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256) grain_chain_kernel(const GrainSegTrack* _
         ++count;
         start = idx;
       }
+      __syncwarp();  // every lane has read the previous state before lane 0 replaces it
       if (lane == 0) {
         s_start = start;
         s_count = count;

@@ -39,6 +39,9 @@
 #ifndef MLX_KS_MINB
 #define MLX_KS_MINB 2      // synthesis CTAs per SM the register allocation is bounded for
 #endif
+#ifndef MLX_KS_PRE1
+#define MLX_KS_PRE1 0      // keep the 15 stage-1 twiddle powers of the inverse FFT in registers
+#endif
 #ifndef MLX_KS_WIN_SMEM
 #define MLX_KS_WIN_SMEM 0  // synthesis window in shared memory instead of 32 registers per thread
 #endif
@@ -730,7 +733,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   const long long b = min(a + (long long)wv.CS, hop_lim);
   const long long flim = min(b + 3, tr.F);  // frames [a, flim) contribute to hops [a, b)
 
-  FftTwiddles<float, NC, +1> twd;
+  FftTwiddles<float, NC, +1, MLX_KS_PRE1 != 0> twd;
   twd.init(t, tb.tw_f);
 #if MLX_KS_WIN_SMEM
   float* s_wsyn = reinterpret_cast<float*>(buf + G * BUF);  // [N]

@@ -68,6 +68,9 @@ __device__ __forceinline__ void colour_ramp(float v, float k, unsigned char* rgb
   rgb[2] = b;
 }
 
+#ifndef MLX_SPEC_PRE1
+#define MLX_SPEC_PRE1 0  // K1r: stage-1 twiddle powers in registers (needs MLX_SPEC_MINB=2 to avoid spills)
+#endif
 #ifndef MLX_SPEC_MINB
 #define MLX_SPEC_MINB 3
 #endif
@@ -249,7 +252,7 @@ spec_frames_kernel(const SpecArgs a, const int fpc) {
   }
 
   C* buf = bufs + g * BUF;
-  FftTwiddles<float, NC, -1> twd;
+  FftTwiddles<float, NC, -1, MLX_SPEC_PRE1 != 0> twd;
   twd.init(t, a.tw_f);
   unsigned mask = 0xffffffffu;
   if constexpr (TPF < 32) mask = ((1u << TPF) - 1u) << (((tid & 31) / TPF) * TPF);

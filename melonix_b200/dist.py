@@ -173,3 +173,34 @@ def run_time_sharded(engine, owns, n_total: int, fft_n: int, hop: int, rate: flo
     lo = shard.left_halo
     out = [(ys[t][lo:lo + owns[t].numel()], peak[t, lb:le], f0[t, lb:le]) for t in range(nt)]
     return out[0] if single else out
+
+
+def bind_to_gpu_numa_node(device: int) -> dict:
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off, so that pinned host
+    buffers allocated afterwards (first touch) and the copy-issuing threads are local to the GPU's
+    PCIe root.  With one process per GPU this keeps the H2D/D2H streams of different ranks off the
+    inter-socket link.  Returns what it did; never raises (no sysfs / no NVML -> no-op)."""
+    import os
+    info = dict(device=device, node=None, cpus=0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(node=node, cpus=len(cpus))
+    except Exception as e:  # noqa: BLE001
+        info["error"] = str(e)
+    return info

@@ -11,12 +11,12 @@
 
 using namespace mlx;
 
-template <typename T, int NC, int DIR, int S>
+template <typename T, int NC, int DIR, int S, bool PRE1 = false>
 struct Emul {
   using F = Fft<T, NC, DIR>;
   using P = FftPlan<NC>;
   static void go(std::vector<cplx<T>>& regs, std::vector<cplx<T>>& buf,
-                 std::vector<FftTwiddles<T, NC, DIR>>& tw) {
+                 std::vector<FftTwiddles<T, NC, DIR, PRE1>>& tw) {
     if constexpr (S < P::NSTAGES) {
       if constexpr (S > 0) {
         // "barrier", then every thread loads, "barrier"
@@ -27,12 +27,12 @@ struct Emul {
       }
       for (int t = 0; t < P::TPF; ++t)
         F::template compute<S>(*reinterpret_cast<cplx<T>(*)[16]>(&regs[t * 16]), buf.data(), t, tw[t]);
-      Emul<T, NC, DIR, S + 1>::go(regs, buf, tw);
+      Emul<T, NC, DIR, S + 1, PRE1>::go(regs, buf, tw);
     }
   }
 };
 
-template <typename T, int NC, int DIR>
+template <typename T, int NC, int DIR, bool PRE1 = false>
 double check() {
   using P = FftPlan<NC>;
   std::vector<cplx<T>> table(NC);
@@ -48,7 +48,7 @@ double check() {
   mlxo_fft_plan_destroy(plan);
 
   std::vector<cplx<T>> regs(P::TPF * 16), buf(P::BUF);
-  std::vector<FftTwiddles<T, NC, DIR>> tw(P::TPF);
+  std::vector<FftTwiddles<T, NC, DIR, PRE1>> tw(P::TPF);
   for (int t = 0; t < P::TPF; ++t) {
     tw[t].init(t, table.data());
     for (int m = 0; m < 16; ++m) {
@@ -56,7 +56,7 @@ double check() {
       regs[t * 16 + m] = cplx<T>{T(in[2 * i]), T(in[2 * i + 1])};
     }
   }
-  Emul<T, NC, DIR, 0>::go(regs, buf, tw);
+  Emul<T, NC, DIR, 0, PRE1>::go(regs, buf, tw);
   double err = 0, nrm = 0;
   for (int t = 0; t < P::TPF; ++t)
     for (int m = 0; m < 16; ++m) {
@@ -73,6 +73,9 @@ int check_all() {
   int bad = 0;
   const double ef = check<float, NC, -1>(), eb = check<float, NC, +1>();
   const double df = check<double, NC, -1>(), db = check<double, NC, +1>();
+  // stage-1 twiddle powers kept in registers: the same product tree, hence the same error
+  const double pf = check<float, NC, -1, true>(), pb = check<float, NC, +1, true>();
+  if (pf != ef || pb != eb) bad = 1;
   std::printf("NC=%5d  float fwd %.2e inv %.2e   double fwd %.2e inv %.2e\n", NC, ef, eb, df, db);
   if (!(ef < 2e-6 && eb < 2e-6 && df < 1e-14 && db < 1e-14)) bad = 1;
   return bad;

@@ -93,10 +93,11 @@ def test_regular_hop_tiled_kernel(engine, oracle, N):
     x = S.vibrato_tone(1.5, seed=3 * N)
     engine.upload_tracks([x])
     engine.use_torch_stream()
-    for hop, first in ((N // 4, 0), (N, 0), (300, 0), (N // 4, 7)):
+    for hop, first, count in ((N // 4, 0, None), (N, 0, None), (300, 0, None), (N // 4, 7, None), (4, 1000, 333),
+                              (N - 4, 3, 5), (N // 4, 40, 1)):
         if hop > N:
             continue
-        F = (x.size + hop - 1) // hop + 5 - first          # five frames past the end of the track
+        F = count or (x.size + hop - 1) // hop + 5 - first  # five frames past the end of the track
         out = torch.empty((F, N // 2), dtype=torch.float32, device="cuda")
         engine.spec_frames_dev(0, N, hop, first, F, out)
         torch.cuda.synchronize()
