@@ -188,3 +188,20 @@ def test_grain_segmentation_golden(engine):
     engine.upload_tracks([x])
     gs, gl = engine.grain_segment()[0]
     assert np.array_equal(gs, g["g_start"]) and np.array_equal(gl, g["g_len"])
+
+
+def test_grain_segmentation_two_hour_track(engine):
+    """BASELINE configs[3] length (2 h at 48 kHz, 345.6 M samples): positions beyond 2^28, ~10.8 M words of
+    crossing bits, ~1300 stage refills in the chain; against the host C++ mirror (the oracle's twin)."""
+    from melonix_b200 import hostlib as H
+    base = S.vibrato_tone(60.0, seed=21)
+    x = np.tile(base, 120)
+    x[1::100003] *= -1.0                      # break the exact periodicity of the tiling
+    assert x.size == 345_600_000
+    engine.upload_tracks([x])
+    gs, gl = engine.grain_segment()[0]
+    hs, hl = H.grain_segment(x)
+    assert gs.size == hs.size > 200_000
+    assert np.array_equal(gs, hs) and np.array_equal(gl, hl)
+    assert int(gs[-1]) > (1 << 28)
+    engine.upload_tracks([np.zeros(16, np.float32)])   # release the 1.4 GB track buffer for later tests
