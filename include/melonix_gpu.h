@@ -157,6 +157,25 @@ MLX_API int mlx_grain_segment(mlx_ctx *ctx, int32_t *const *g_start, int32_t *co
 MLX_API int mlx_grain_segment_dev(mlx_ctx *ctx, int32_t *const *g_start_dev, int32_t *const *g_len_dev,
                           int cap, int32_t *counts_dev);
 
+/* ---- waveform min/max pyramid (replaces App::calcPicks, reference app.cpp:347-378, and
+ *      App::getMinMaxFromRange, app.cpp:380-426 -- the waveform display's level-of-detail cache) ---- */
+/* Level l holds floor(n / 2^(l+1)) entries (min, max) over samples [i 2^(l+1), (i+1) 2^(l+1)); levels
+ * exist while n > 2^(l+1), exactly the reference's `picks` (app.hpp:42).  All levels are stored back to
+ * back as float pairs; mlx_picks_layout fills level_off[levels + 1] (first entry of each level, in
+ * pairs) and returns the total number of pairs.  Both are pure host functions of n. */
+MLX_API int mlx_picks_levels(int64_t n);
+MLX_API int64_t mlx_picks_layout(int64_t n, int64_t *level_off);
+/* Builds the pyramid of an uploaded track: pairs = [total][2] floats (host / device memory). */
+MLX_API int mlx_picks_build(mlx_ctx *ctx, int track, float *pairs);
+MLX_API int mlx_picks_build_dev(mlx_ctx *ctx, int track, float *pairs_dev);
+/* Every uploaded track in one launch: pairs_dev = host array of ntracks device pointers. */
+MLX_API int mlx_picks_build_all_dev(mlx_ctx *ctx, float *const *pairs_dev);
+/* getMinMaxFromRange for `count` ranges (start, end) at once: out = [count][2] (min, max), including
+ * the reference's behaviour at the edges (empty and out-of-range ranges give (0, 0) or the single
+ * sample, app.cpp:382-396; the block that contains `start` is taken whole, app.cpp:399-408).  The
+ * pyramid of `track` is built on first use and cached until the next upload. */
+MLX_API int mlx_minmax_ranges(mlx_ctx *ctx, int track, const int32_t *start_end, int count, float *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,13 @@ def lib() -> C.CDLL:
     L.mlx_pv_process_host.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(i64), i32,
                                       C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mlx_grain_render.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    L.mlx_picks_levels.argtypes = [i64]
+    L.mlx_picks_layout.argtypes = [i64, vp]
+    L.mlx_picks_layout.restype = i64
+    L.mlx_picks_build.argtypes = [vp, i32, vp]
+    L.mlx_picks_build_dev.argtypes = [vp, i32, vp]
+    L.mlx_picks_build_all_dev.argtypes = [vp, C.POINTER(vp)]
+    L.mlx_minmax_ranges.argtypes = [vp, i32, vp, i32, vp]
     L.mlx_grain_segment.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32, vp]
     L.mlx_grain_segment_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32, vp]
     _lib = L

@@ -101,6 +101,8 @@ struct mlx_ctx {
   DevBuf jobs, spec_out, spec_rgb;
   DevBuf g_i32a, g_i32b, g_f32a, g_f32b, g_i64, g_out, g_out16;
   DevBuf seg_bits, seg_desc, seg_rows, seg_count;  // grain segmentation scratch
+  DevBuf picks, picks_ranges, picks_out, picks_desc;  // min/max pyramid of track `picks_track` + query staging
+  int picks_track = -1;
   // pinned staging ring for per-call descriptors / tables: a slot is reused only after the copies
   // that read it have completed (event), so launches never wait on the host.
   struct Slot {
@@ -204,6 +206,7 @@ int ensure_tables(mlx_ctx* c, int N, bool want_pv, Tables** out) {
 int layout_tracks(mlx_ctx* c, const int64_t* n, int ntracks) {
   if (ntracks <= 0 || !n) return fail(MLX_ERR_INVALID, "ntracks must be > 0");
   c->tracks.assign(ntracks, Track{});
+  c->picks_track = -1;  // a cached pyramid belongs to the previous upload
   size_t off = 0;
   for (int t = 0; t < ntracks; ++t) {
     if (n[t] < 0 || n[t] > (int64_t)0x7fffffff - 65536)
@@ -457,7 +460,7 @@ void mlx_destroy(mlx_ctx* c) {
   for (DevBuf* b : {&c->gk, &c->track_buf, &c->smag, &c->lacc, &c->tot, &c->totc, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
                     &c->out_wav, &c->out_peak, &c->out_f0, &c->jobs, &c->spec_out, &c->spec_rgb, &c->g_i32a,
                     &c->g_i32b, &c->g_f32a, &c->g_f32b, &c->g_i64, &c->g_out, &c->g_out16, &c->seg_bits,
-                    &c->seg_desc, &c->seg_rows, &c->seg_count})
+                    &c->seg_desc, &c->seg_rows, &c->seg_count, &c->picks, &c->picks_ranges, &c->picks_out, &c->picks_desc})
     b->release();
   for (auto& kv : c->tables)
     for (DevBuf* b : {&kv.second.tw_d, &kv.second.twr_d, &kv.second.tw_f, &kv.second.twr_f, &kv.second.win,
@@ -972,6 +975,122 @@ int mlx_grain_segment(mlx_ctx* c, int32_t* const* g_start, int32_t* const* g_len
     CK(cudaMemcpyAsync(g_start[t], ps[t], sizeof(int32_t) * m, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(g_len[t], pl[t], sizeof(int32_t) * m, cudaMemcpyDeviceToHost, c->stream));
   }
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ picks
+int mlx_picks_levels(int64_t n) {
+  int lvl = 0;
+  while (n > ((int64_t)1 << (lvl + 1))) ++lvl;  // reference app.cpp:352, :365
+  return lvl;
+}
+
+int64_t mlx_picks_layout(int64_t n, int64_t* level_off) {
+  const int L = mlx_picks_levels(n);
+  int64_t off = 0;
+  for (int l = 0; l < L; ++l) {
+    if (level_off) level_off[l] = off;
+    off += n >> (l + 1);  // reference app.cpp:356, :369
+  }
+  if (level_off) level_off[L] = off;
+  return off;
+}
+
+static int picks_fill_args(mlx_ctx* c, int track, float* pairs_dev, PicksArgs* a) {
+  if (!c) return fail(MLX_ERR_INVALID, "ctx is null");
+  if (track < 0 || track >= (int)c->tracks.size()) return fail(MLX_ERR_STATE, "track not uploaded");
+  a->x = c->track_ptr(track);
+  a->n = c->tracks[track].n;
+  a->levels = mlx_picks_levels(a->n);
+  int64_t off[33];
+  mlx_picks_layout(a->n, off);
+  for (int l = 0; l <= a->levels; ++l) a->level_off[l] = off[l];
+  a->pairs = reinterpret_cast<float2*>(pairs_dev);
+  return MLX_OK;
+}
+
+// pyramids of tracks [first, first + count) in one launch; pairs_dev[i] belongs to track first + i
+static int picks_build_range(mlx_ctx* c, int first, int count, float* const* pairs_dev) {
+  CK(cudaSetDevice(c->device));
+  CK(c->picks_desc.reserve(sizeof(PicksArgs) * count));
+  mlx_ctx::Slot* slot = nullptr;
+  int rc = acquire_slot(c, sizeof(PicksArgs) * count, &slot);
+  if (rc) return rc;
+  PicksArgs* d = static_cast<PicksArgs*>(slot->p);
+  long long max_n = 0;
+  int max_levels = 0;
+  for (int i = 0; i < count; ++i) {
+    rc = picks_fill_args(c, first + i, pairs_dev[i], &d[i]);
+    if (rc) return rc;
+    if (d[i].levels > 0 && !pairs_dev[i]) return fail(MLX_ERR_INVALID, "null argument");
+    max_n = std::max(max_n, d[i].n);
+    max_levels = std::max(max_levels, d[i].levels);
+  }
+  CK(cudaMemcpyAsync(c->picks_desc.p, d, sizeof(PicksArgs) * count, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(slot->done, c->stream));
+  c->mark(4);
+  CK(launch_picks_build(static_cast<const PicksArgs*>(c->picks_desc.p), count, max_n, max_levels, c->stream));
+  c->mark(-1);
+  if (max_levels > 0) c->launches += max_levels > 12 ? 2 : 1;
+  return MLX_OK;
+}
+
+int mlx_picks_build_dev(mlx_ctx* c, int track, float* pairs_dev) {
+  if (!c) return fail(MLX_ERR_INVALID, "ctx is null");
+  if (track < 0 || track >= (int)c->tracks.size()) return fail(MLX_ERR_STATE, "track not uploaded");
+  return picks_build_range(c, track, 1, &pairs_dev);
+}
+
+int mlx_picks_build_all_dev(mlx_ctx* c, float* const* pairs_dev) {
+  if (!c || !pairs_dev) return fail(MLX_ERR_INVALID, "null argument");
+  if (c->tracks.empty()) return fail(MLX_ERR_STATE, "no tracks uploaded");
+  return picks_build_range(c, 0, (int)c->tracks.size(), pairs_dev);
+}
+
+// builds (once per upload and track) the pyramid the host entry points work on
+static int picks_ensure(mlx_ctx* c, int track, PicksArgs* a) {
+  int rc = picks_fill_args(c, track, nullptr, a);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  const size_t total = (size_t)a->level_off[a->levels];
+  if (c->picks_track != track) {
+    CK(c->picks.reserve(sizeof(float) * 2 * std::max<size_t>(total, 1)));
+    rc = mlx_picks_build_dev(c, track, static_cast<float*>(c->picks.p));
+    if (rc) return rc;
+    c->picks_track = track;
+  }
+  a->pairs = static_cast<float2*>(c->picks.p);
+  return MLX_OK;
+}
+
+int mlx_picks_build(mlx_ctx* c, int track, float* pairs) {
+  PicksArgs a{};
+  int rc = picks_ensure(c, track, &a);
+  if (rc) return rc;
+  const size_t total = (size_t)a.level_off[a.levels];
+  if (total == 0) return MLX_OK;
+  if (!pairs) return fail(MLX_ERR_INVALID, "null argument");
+  CK(cudaMemcpyAsync(pairs, c->picks.p, sizeof(float) * 2 * total, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MLX_OK;
+}
+
+int mlx_minmax_ranges(mlx_ctx* c, int track, const int32_t* start_end, int count, float* out) {
+  if (count < 0 || (count > 0 && (!start_end || !out))) return fail(MLX_ERR_INVALID, "bad argument");
+  PicksArgs a{};
+  int rc = picks_ensure(c, track, &a);
+  if (rc) return rc;
+  if (count == 0) return MLX_OK;
+  CK(c->picks_ranges.reserve(sizeof(int32_t) * 2 * (size_t)count));
+  CK(c->picks_out.reserve(sizeof(float) * 2 * (size_t)count));
+  CK(cudaMemcpyAsync(c->picks_ranges.p, start_end, sizeof(int32_t) * 2 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+  c->mark(4);
+  CK(launch_minmax_ranges(a, static_cast<const int*>(c->picks_ranges.p), count, static_cast<float*>(c->picks_out.p),
+                          c->stream));
+  c->mark(-1);
+  c->launches += 1;
+  CK(cudaMemcpyAsync(out, c->picks_out.p, sizeof(float) * 2 * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return MLX_OK;
 }

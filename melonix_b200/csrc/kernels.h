@@ -121,4 +121,17 @@ struct GrainSegTrack {
 cudaError_t launch_grain_segment(const GrainSegTrack* tracks_dev, int ntracks, long long max_words, int cap,
                                  cudaStream_t st);
 
+// ---- waveform min/max pyramid (K9)
+struct PicksArgs {
+  const float* x;          // sample 0 of the padded device copy
+  long long n;
+  float2* pairs;           // all levels back to back, (min, max) per entry
+  long long level_off[32]; // first entry of level l (in pairs); [levels] = total
+  int levels;              // levels exist while n > 2^(l+1) (reference app.cpp:352, :365)
+};
+cudaError_t launch_picks_build(const PicksArgs* tracks_dev, int ntracks, long long max_n, int max_levels,
+                               cudaStream_t st);  // one launch for all tracks (blockIdx.y = track)
+cudaError_t launch_minmax_ranges(const PicksArgs& a, const int* start_end_dev, int count, float* out_dev,
+                                 cudaStream_t st);
+
 }  // namespace mlx

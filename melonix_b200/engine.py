@@ -193,6 +193,36 @@ class Engine:
         self._lens = [size(t) for t in tracks]
 
     # ------------------------------------------------------------------ grain path
+    # ------------------------------------------------------------------ waveform pyramid
+    def picks_layout(self, n: int) -> np.ndarray:
+        """level_off[levels + 1] (in pairs) of the min/max pyramid of an n-sample track (app.cpp:347-378)."""
+        L = int(self._L.mlx_picks_levels(n))
+        off = np.zeros(L + 1, np.int64)
+        self._L.mlx_picks_layout(n, off.ctypes.data)
+        return off
+
+    def picks_build(self, track: int):
+        """(pairs [total, 2] float32, level_off) of an uploaded track -- App::calcPicks on the GPU."""
+        off = self.picks_layout(int(self._L.mlx_track_len(self._h, track)))
+        pairs = np.zeros((max(int(off[-1]), 1), 2), np.float32)
+        check(self._L.mlx_picks_build(self._h, track, pairs.ctypes.data))
+        return pairs[:int(off[-1])], off
+
+    def picks_build_dev(self, track: int, pairs) -> None:
+        assert pairs.is_cuda and pairs.is_contiguous()
+        check(self._L.mlx_picks_build_dev(self._h, track, pairs.data_ptr()))
+
+    def picks_build_all_dev(self, pairs_list) -> None:
+        """One launch for all uploaded tracks; pairs_list[t]: float32 CUDA tensor [total_t, 2]."""
+        check(self._L.mlx_picks_build_all_dev(self._h, ptr_array([p.data_ptr() for p in pairs_list])))
+
+    def minmax_ranges(self, track: int, ranges) -> np.ndarray:
+        """App::getMinMaxFromRange (app.cpp:380-426) for every (start, end) row of `ranges`."""
+        r = np.ascontiguousarray(ranges, np.int32).reshape(-1, 2)
+        out = np.zeros((r.shape[0], 2), np.float32)
+        check(self._L.mlx_minmax_ranges(self._h, track, r.ctypes.data, r.shape[0], out.ctypes.data))
+        return out
+
     def grain_segment(self, cap: int | None = None):
         """Zero-crossing grain segmentation of every uploaded track on the GPU (App::preproc,
         reference app.cpp:156-235).  Returns [(g_start, g_len)] per track (int32 arrays)."""

@@ -15,6 +15,9 @@
  *                     App::process (app.cpp:294-345), App::exportWav (app.cpp:1194-1215) and the
  *                     marker warp maps (app.cpp:1020-1122).  parity unpinned (app.cpp needs
  *                     SDL/ImGui/FFmpeg/ser to build; KAT-4/KAT-5 are the analytic anchors).
+ *   - mlxo_picks_* / mlxo_minmax_ranges : restate App::calcPicks / App::getMinMaxFromRange
+ *                     (reference app.cpp:347-426).  parity unpinned (same reason); brute-force
+ *                     min/max over aligned ranges is the analytic anchor.
  *   - mlxo_pv_*     : NOT IN REFERENCE.  Double-precision restatement of PV-spec v1 (DESIGN.md,
  *                     from SURVEY.md Appendix A).  parity unpinned by reference: self-consistency
  *                     target only.
@@ -80,6 +83,14 @@ int64_t mlxo_grain_export(const float *wav, int64_t n, int sampleRate, const mlx
                           int16_t *pcm16, int64_t cap, int32_t *s_gstart, int32_t *s_glen,
                           float *s_rate, int64_t *s_out_off, float *s_next, int *nsched,
                           int cap_sched);
+
+/* ---- waveform min/max pyramid (reference app.cpp:347-378 calcPicks, :380-426 getMinMaxFromRange) ---- */
+int mlxo_picks_levels(int64_t n);
+/* level_off[levels + 1] in pairs; returns the total number of pairs */
+int64_t mlxo_picks_layout(int64_t n, int64_t *level_off);
+void mlxo_picks_build(const float *wav, int64_t n, float *pairs /*[total][2]*/, const int64_t *level_off);
+void mlxo_minmax_ranges(const float *wav, int64_t n, const float *pairs, const int64_t *level_off,
+                        const int32_t *start_end, int count, float *out /*[count][2]*/);
 
 int mlxo_num_threads(void);
 

@@ -19,8 +19,8 @@ REF_SPECTR_SIZE = 32768  # reference spec.cpp:8
 
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
-    if force or not _LIB.exists() or (Path("/root/reference/spec.cpp").exists() and not _REF.exists()):
-        subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
+    del force  # make is cheap when everything is up to date, and a stale library must never be used
+    subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
 
 
 _lib = None
@@ -177,6 +177,31 @@ def grain_segment(wav: np.ndarray):
     ng = lib().mlxo_grain_segment(_ptr(wav), C.c_int64(wav.size), _ptr(gs), _ptr(gl), C.c_int(cap))
     assert ng <= cap
     return gs[:ng].copy(), gl[:ng].copy()
+
+
+def picks_build(wav: np.ndarray):
+    """calcPicks (app.cpp:347-378): returns (pairs [total, 2] float32, level_off [levels + 1] int64)."""
+    wav = np.ascontiguousarray(wav, np.float32)
+    L = lib().mlxo_picks_levels(C.c_int64(wav.size))
+    off = np.zeros(L + 1, np.int64)
+    lib().mlxo_picks_layout.restype = C.c_int64
+    total = lib().mlxo_picks_layout(C.c_int64(wav.size), off.ctypes.data_as(C.c_void_p))
+    pairs = np.zeros((max(total, 1), 2), np.float32)
+    lib().mlxo_picks_build(_ptr(wav), C.c_int64(wav.size), _ptr(pairs), off.ctypes.data_as(C.c_void_p))
+    return pairs[:total], off
+
+
+def minmax_ranges(wav: np.ndarray, pairs: np.ndarray, level_off: np.ndarray, ranges: np.ndarray) -> np.ndarray:
+    """getMinMaxFromRange (app.cpp:380-426) for every (start, end) row of `ranges`."""
+    wav = np.ascontiguousarray(wav, np.float32)
+    pairs = np.ascontiguousarray(pairs, np.float32)
+    ranges = np.ascontiguousarray(ranges, np.int32)
+    out = np.zeros((ranges.shape[0], 2), np.float32)
+    pp = pairs if pairs.size else np.zeros((1, 2), np.float32)
+    lib().mlxo_minmax_ranges(_ptr(wav) if wav.size else None, C.c_int64(wav.size), _ptr(pp),
+                             np.ascontiguousarray(level_off, np.int64).ctypes.data_as(C.c_void_p), _ptr(ranges),
+                             C.c_int(ranges.shape[0]), _ptr(out))
+    return out
 
 
 def time2sample(markers, sr: int, val: float) -> int:

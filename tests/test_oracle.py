@@ -146,3 +146,36 @@ def test_colormap_matches_numpy_restatement(oracle):
             lk = int(np.float32(np.float32(t - np.float32(170)) * np.float32(3)))
             exp[i] = (lk, int(t), lk)
     assert np.array_equal(oracle.colormap(v, float(k)), exp)
+
+
+def test_picks_oracle_against_brute_force(oracle):
+    """Restatement of App::calcPicks / getMinMaxFromRange (app.cpp:347-426): every level equals the
+    brute-force min/max of its blocks, aligned range queries are exact, and the reference's edge
+    behaviour (empty / out-of-range ranges, app.cpp:382-396) is reproduced."""
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 3, 4, 5, 8, 9, 1000, 4097, 100003):
+        x = rng.standard_normal(n).astype(np.float32)
+        pairs, off = oracle.picks_build(x)
+        L = len(off) - 1
+        assert L == sum(1 for l in range(40) if n > (1 << (l + 1)))
+        for l in range(L):
+            cnt = n >> (l + 1)
+            assert off[l + 1] - off[l] == cnt
+            blk = x[:cnt << (l + 1)].reshape(cnt, -1)
+            assert np.array_equal(pairs[off[l]:off[l + 1], 0], blk.min(1))
+            assert np.array_equal(pairs[off[l]:off[l + 1], 1], blk.max(1))
+        if n > 16:
+            r = []
+            for _ in range(200):
+                l = int(rng.integers(1, int(np.log2(n))))
+                i = int(rng.integers(0, n >> l))
+                if ((i + 1) << l) < n:
+                    r.append((i << l, (i + 1) << l))
+            r = np.array(r, np.int32)
+            bf = np.array([[x[s:e].min(), x[s:e].max()] for s, e in r], np.float32)
+            assert np.array_equal(oracle.minmax_ranges(x, pairs, off, r), bf)
+            edge = np.array([[5, 5], [7, 3], [n, n], [-3, 10], [10, -3], [0, n], [3, 4]], np.int32)
+            e = oracle.minmax_ranges(x, pairs, off, edge)
+            assert np.array_equal(e[0], [x[5], x[5]]) and np.array_equal(e[1], [x[7], x[7]])
+            assert not e[2].any() and not e[3].any() and not e[4].any() and not e[5].any()
+            assert np.array_equal(e[6], [x[3], x[3]])
