@@ -177,5 +177,6 @@ def test_picks_oracle_against_brute_force(oracle):
             edge = np.array([[5, 5], [7, 3], [n, n], [-3, 10], [10, -3], [0, n], [3, 4]], np.int32)
             e = oracle.minmax_ranges(x, pairs, off, edge)
             assert np.array_equal(e[0], [x[5], x[5]]) and np.array_equal(e[1], [x[7], x[7]])
-            assert not e[2].any() and not e[3].any() and not e[4].any() and not e[5].any()
+            assert not e[2].any() and not e[3].any() and not e[5].any()
+            assert np.array_equal(e[4], [x[10], x[10]])   # start >= end is tested first (app.cpp:382)
             assert np.array_equal(e[6], [x[3], x[3]])
