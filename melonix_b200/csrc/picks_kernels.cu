@@ -4,8 +4,8 @@
 // Level l holds floor(n / 2^(l+1)) pairs (min, max) over samples [i 2^(l+1), (i+1) 2^(l+1)); levels
 // exist while n > 2^(l+1).  The reference builds level l from level l-1 with std::min / std::max on
 // the (first, second) halves, re-reading each level from memory; here one CTA reduces a tile of 4096
-// samples through levels 0..11 in registers (16 samples per thread), warp shuffles and one shared-memory
-// hop, writing every level as it appears -- each sample is read once (4 B) and the pyramid written once
+// samples through levels 0..11 in registers (four float4 per thread, lane-contiguous), warp shuffles and
+// one shared-memory hop, writing every level as it appears -- each sample is read once (4 B) and the pyramid written once
 // (8 B per sample in total): an HBM-bound streaming kernel.  The few levels above the tile are
 // finished by one CTA.  std::min(a, b) is (b < a) ? b : a and std::max(a, b) is (a < b) ? b : a with
 // a = the LOWER-indexed half: that order decides the result for NaN and signed zeros and is kept.
@@ -23,7 +23,7 @@ constexpr int kPickTile = 4096;      // samples per CTA
 constexpr int kPickTileLevels = 12;  // levels 0..11 are complete inside a tile
 
 __global__ void __launch_bounds__(256) picks_tile_kernel(const PicksArgs* __restrict__ tracks) {
-  __shared__ float2 s_warp[8];
+  __shared__ float2 s_part[32];  // level-6 entries (128 samples each) of the tile, in sample order
   __shared__ PicksArgs a;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long tile = blockIdx.x;
@@ -31,72 +31,69 @@ __global__ void __launch_bounds__(256) picks_tile_kernel(const PicksArgs* __rest
   if (tid < (int)(sizeof(PicksArgs) / sizeof(int)))
     reinterpret_cast<int*>(&a)[tid] = reinterpret_cast<const int*>(tracks + blockIdx.y)[tid];
   __syncthreads();
-  const long long base = tile * kPickTile + tid * 16;
-  // 16 consecutive samples; a span that crosses n produces no entry, so its values never matter
-  float s[16];
-  if (base + 16 <= a.n) {
+  const bool aligned = (reinterpret_cast<unsigned long long>(a.pairs) & 15ull) == 0ull;  // level 0 starts at pairs
+  // Lane-contiguous I/O: in round v the thread takes float4 number f = v*256 + tid of the tile (samples
+  // 4f .. 4f+3), so every load and every store of levels 0 and 1 is one contiguous run per warp.
+  // A span that crosses n produces no entry, so the values read past n never matter.
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(a.x + base) + v);
-      s[4 * v] = q.x; s[4 * v + 1] = q.y; s[4 * v + 2] = q.z; s[4 * v + 3] = q.w;
+  for (int v = 0; v < 4; ++v) {
+    const int f = v * 256 + tid;
+    const long long s0 = tile * kPickTile + 4LL * f;
+    float4 q;
+    if (s0 + 4 <= a.n) {
+      q = __ldg(reinterpret_cast<const float4*>(a.x + s0));
+    } else {
+      q.x = s0 < a.n ? __ldg(a.x + s0) : 0.f;
+      q.y = s0 + 1 < a.n ? __ldg(a.x + s0 + 1) : 0.f;
+      q.z = s0 + 2 < a.n ? __ldg(a.x + s0 + 2) : 0.f;
+      q.w = 0.f;
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) s[i] = (base + i < a.n) ? __ldg(a.x + base + i) : 0.f;
-  }
-  float2 p[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) p[i] = make_float2(smin(s[2 * i], s[2 * i + 1]), smax(s[2 * i], s[2 * i + 1]));
-  // levels 0..3 from registers: level l has 8 >> l entries per thread
-#pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    const int per = 8 >> l;
-    if (l < a.levels) {
-      const long long first = tile * (kPickTile >> (l + 1)) + (long long)tid * per;
-      const long long cnt = a.n >> (l + 1);
-      float2* out = a.pairs + a.level_off[l] + first;
-      if (first + per <= cnt && per >= 2 && (reinterpret_cast<unsigned long long>(out) & 15ull) == 0ull) {
-#pragma unroll
-        for (int i = 0; i < per; i += 2)
-          *reinterpret_cast<float4*>(out + i) = make_float4(p[i].x, p[i].y, p[i + 1].x, p[i + 1].y);
+    const float2 p0 = make_float2(smin(q.x, q.y), smax(q.x, q.y));
+    const float2 p1 = make_float2(smin(q.z, q.w), smax(q.z, q.w));
+    if (a.levels > 0) {  // level 0: entries 2f, 2f+1 of the tile
+      const long long idx = tile * (kPickTile >> 1) + 2LL * f;
+      const long long cnt = a.n >> 1;
+      float2* out = a.pairs + a.level_off[0] + idx;
+      if (idx + 2 <= cnt && aligned) {
+        *reinterpret_cast<float4*>(out) = make_float4(p0.x, p0.y, p1.x, p1.y);
       } else {
-#pragma unroll
-        for (int i = 0; i < per; ++i)
-          if (first + i < cnt) out[i] = p[i];
+        if (idx < cnt) out[0] = p0;
+        if (idx + 1 < cnt) out[1] = p1;
       }
     }
-#pragma unroll
-    for (int i = 0; i < per / 2; ++i) p[i] = comb(p[2 * i], p[2 * i + 1]);
-  }
-  // p[0] is now the thread's level-3 entry (16 samples).  Levels 4..8: pairs of lanes, the lower lane
-  // holds the first half.
-  float2 v = p[0];
-#pragma unroll
-  for (int sft = 0; sft < 5; ++sft) {
-    const int l = 4 + sft;
-    float2 o;
-    o.x = __shfl_down_sync(0xffffffffu, v.x, 1 << sft);
-    o.y = __shfl_down_sync(0xffffffffu, v.y, 1 << sft);
-    v = comb(v, o);
-    if (l < a.levels && (lane & ((2 << sft) - 1)) == 0) {
-      const long long idx = tile * (kPickTile >> (l + 1)) + (tid >> (sft + 1));
-      if (idx < (a.n >> (l + 1))) a.pairs[a.level_off[l] + idx] = v;
+    float2 e = comb(p0, p1);
+    if (a.levels > 1) {  // level 1: entry f
+      const long long idx = tile * (kPickTile >> 2) + f;
+      if (idx < (a.n >> 2)) a.pairs[a.level_off[1] + idx] = e;
     }
-  }
-  if (lane == 0) s_warp[warp] = v;  // level 8: 512 samples per warp
-  __syncthreads();
-  if (warp == 0) {
-    v = s_warp[lane & 7];
+    // levels 2..6: pairs of lanes, the lower lane holds the first half
 #pragma unroll
-    for (int sft = 0; sft < 3; ++sft) {
-      const int l = 9 + sft;
+    for (int sft = 0; sft < 5; ++sft) {
+      const int l = 2 + sft;
       float2 o;
-      o.x = __shfl_down_sync(0xffffffffu, v.x, 1 << sft);
-      o.y = __shfl_down_sync(0xffffffffu, v.y, 1 << sft);
-      v = comb(v, o);
-      if (l < a.levels && lane < 8 && (lane & ((2 << sft) - 1)) == 0) {
+      o.x = __shfl_down_sync(0xffffffffu, e.x, 1 << sft);
+      o.y = __shfl_down_sync(0xffffffffu, e.y, 1 << sft);
+      e = comb(e, o);
+      if (l < a.levels && (lane & ((2 << sft) - 1)) == 0) {
+        const long long idx = tile * (kPickTile >> (l + 1)) + (f >> (sft + 1));
+        if (idx < (a.n >> (l + 1))) a.pairs[a.level_off[l] + idx] = e;
+      }
+    }
+    if (lane == 0) s_part[v * 8 + warp] = e;  // level 6: samples [128 (v*8 + warp), +128) of the tile
+  }
+  __syncthreads();
+  if (warp == 0) {  // levels 7..11 from the 32 level-6 entries
+    float2 e = s_part[lane];
+#pragma unroll
+    for (int sft = 0; sft < 5; ++sft) {
+      const int l = 7 + sft;
+      float2 o;
+      o.x = __shfl_down_sync(0xffffffffu, e.x, 1 << sft);
+      o.y = __shfl_down_sync(0xffffffffu, e.y, 1 << sft);
+      e = comb(e, o);
+      if (l < a.levels && (lane & ((2 << sft) - 1)) == 0) {
         const long long idx = tile * (kPickTile >> (l + 1)) + (lane >> (sft + 1));
-        if (idx < (a.n >> (l + 1))) a.pairs[a.level_off[l] + idx] = v;
+        if (idx < (a.n >> (l + 1))) a.pairs[a.level_off[l] + idx] = e;
       }
     }
   }
