@@ -16,30 +16,59 @@
 
 namespace mlx {
 
+constexpr int kGrainSegment = 256 * 16;  // output samples per CTA step
+
 __global__ void __launch_bounds__(256) grain_kernel(const GrainArgs a) {
+  __shared__ int s_g0;
   const long long rendered = a.out_off[a.ngrains];
-  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < a.total;
-       o += (long long)gridDim.x * blockDim.x) {
-    float v = 0.f;  // tail: preferredGrainSize zeros pushed when no grain is left (app.cpp:303-309)
-    if (o < rendered) {
-      int lo = 0, hi = a.ngrains - 1;  // largest g with out_off[g] <= o
+  // A CTA renders contiguous segments of the output.  The schedule row of the segment's first sample
+  // is found once (binary search, thread 0); a segment spans only a few rows (a row is ~1500 / rate
+  // samples), so every thread then walks forward from it instead of searching per sample.
+  for (long long seg = (long long)blockIdx.x * kGrainSegment; seg < a.total; seg += (long long)gridDim.x * kGrainSegment) {
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = a.ngrains - 1;  // largest g with out_off[g] <= seg (rows are non-empty in output time)
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (a.out_off[mid] <= o) lo = mid; else hi = mid - 1;
+        if (a.out_off[mid] <= seg) lo = mid; else hi = mid - 1;
       }
-      const int i = (int)(o - a.out_off[lo]);
-      const float p = __fadd_rn(__fmul_rn((float)i, a.g_rate[lo]), 0.f);
-      const float idxF = truncf(p);
-      const float frac = __fsub_rn(p, idxF);
-      const int idx = (int)idxF;
-      const float* gx = a.x + a.g_start[lo];
-      const float x0 = gx[idx];
-      const float x1 = (idx + 1 < a.g_len[lo]) ? gx[idx + 1] : a.g_next[lo];
-      v = __fadd_rn(__fmul_rn(__fsub_rn(1.f, frac), x0), __fmul_rn(frac, x1));
+      s_g0 = lo;
     }
-    if (a.out) a.out[o] = v;
-    if (a.out_i16) a.out_i16[o] = (short)__double2int_rz((double)v * 32767.);
+    __syncthreads();
+    int g = s_g0;
+    long long next_off = a.ngrains > 0 ? a.out_off[g + 1] : 0;
+#pragma unroll 4
+    for (int j = 0; j < kGrainSegment / 256; ++j) {
+      const long long o = seg + threadIdx.x + 256 * j;
+      if (o >= a.total) break;
+      float v = 0.f;  // tail: preferredGrainSize zeros pushed when no grain is left (app.cpp:303-309)
+      if (o < rendered) {
+        while (o >= next_off) {  // rows with zero output samples are skipped like the binary search did
+          ++g;
+          next_off = a.out_off[g + 1];
+        }
+        const int i = (int)(o - a.out_off[g]);
+        const float p = __fadd_rn(__fmul_rn((float)i, a.g_rate[g]), 0.f);
+        const float idxF = truncf(p);
+        const float frac = __fsub_rn(p, idxF);
+        const int idx = (int)idxF;
+        const float* gx = a.x + a.g_start[g];
+        const float x0 = gx[idx];
+        const float x1 = (idx + 1 < a.g_len[g]) ? gx[idx + 1] : a.g_next[g];
+        v = __fadd_rn(__fmul_rn(__fsub_rn(1.f, frac), x0), __fmul_rn(frac, x1));
+      }
+      if (a.out) a.out[o] = v;
+      if (a.out_i16) a.out_i16[o] = (short)__double2int_rz((double)v * 32767.);
+    }
+    __syncthreads();  // s_g0 is rewritten by the next segment
   }
+}
+
+cudaError_t launch_grain(const GrainArgs& a, cudaStream_t st) {
+  if (a.total <= 0) return cudaSuccess;
+  long long blocks = (a.total + kGrainSegment - 1) / kGrainSegment;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  grain_kernel<<<(int)blocks, 256, 0, st>>>(a);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -195,12 +224,5 @@ cudaError_t launch_grain_segment(const GrainSegTrack* tracks_dev, int ntracks, l
   return cudaGetLastError();
 }
 
-cudaError_t launch_grain(const GrainArgs& a, cudaStream_t st) {
-  if (a.total <= 0) return cudaSuccess;
-  long long blocks = (a.total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  grain_kernel<<<(int)blocks, 256, 0, st>>>(a);
-  return cudaGetLastError();
-}
 
 }  // namespace mlx

@@ -10,6 +10,7 @@ python bench.py > $o/final_bench_n1.json 2> $o/final_bench_n1.err; tail -c 600 $
 python tools/extra_bench.py > $o/final_extra.json 2> $o/final_extra.err
 python tools/seg_probe.py > $o/final_seg_probe.log 2>&1; cat $o/final_seg_probe.log
 python tools/picks_probe.py > $o/final_picks_probe.log 2>&1; cat $o/final_picks_probe.log
+python tools/grain_probe.py > $o/final_grain_probe.log 2>&1; cat $o/final_grain_probe.log
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"pv_|spec_|grain_" -c 60 --csv --log-file $o/final_launches_bench.csv \
   python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $o/final_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pv_ -s 9 -c 3 -o $o/final_prof_pv \
