@@ -129,7 +129,8 @@ spec_kernel(const SpecArgs a) {
         if (dist > 0) {
           float w;
           if (Cfg::TAB && dist <= N) w = s_decay[dist];
-          else w = expf(-2.5e-4f * (float)(int)dist);
+          else if (dist <= N) w = __ldg(a.decay + dist);  // fftN > 8192: the same host table, through L1/L2
+          else w = expf(-2.5e-4f * (float)(int)dist);      // only for jobs with end < start
           s = __fmul_rn(w, s);
         }
         v[c] = s;
