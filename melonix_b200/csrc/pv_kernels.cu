@@ -5,14 +5,17 @@
 // reference's Spec jobs (spec.cpp:47, spec-cache.cpp:63-65).
 //
 //   pv_analyze_kernel  K_A  one CTA = one chunk of consecutive frames of one track, G frames per
-//                           batch.  TMA bulk load of the batch's sample tile -> Hann window ->
+//                           batch (256 threads x 2 CTAs per SM for fftN <= 2048, 512 x 1 beyond).
+//                           TMA bulk load of the batch's sample tile -> Hann window ->
 //                           FP64 real FFT (N/2-point complex Stockham in shared memory) ->
 //                           d = arg(X_f conj(X_{f-1}) (-i)^k) -> magnitude, peak bin, f0 ->
-//                           bin-shift gather -> exact uint32 phase increments, chunk-local scan.
+//                           bin shift with per-bin launch constants -> exact uint32 phase
+//                           increments, chunk-local scan.
 //   pv_scan_kernel          exclusive scan of the chunk totals per (track, bin).
-//   pv_synth_kernel    K_S  theta = prefix + local sum -> Y = smag e^{i theta} -> FP32 inverse real
-//                           FFT -> synthesis window -> atomics-free overlap-add in shared memory
-//                           (fixed ascending-frame summation order) -> float4 stores.
+//   pv_synth_kernel    K_S  theta = prefix + local sum -> Y = smag e^{i theta} (MUFU sin/cos of the
+//                           exact integer phase) -> FP32 inverse real FFT -> synthesis window ->
+//                           atomics-free overlap-add (fixed ascending-frame summation order, three
+//                           pending hops in registers) -> float2 stores.
 //
 // Why FP64 in K_A: the wrapped phase difference has a cut at +-pi; a frame whose FP32 spectrum
 // lands on the other side of the cut than the oracle's shifts that bin's accumulated phase by
