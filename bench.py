@@ -241,8 +241,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # keeps stdout to the one JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (any NCCL_DEBUG level >= VERSION) to stdout: keep stdout to the one
+        # JSON line by sending NCCL's log to stderr instead of changing its level
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
