@@ -121,3 +121,25 @@ def test_bench_reference_arm_contract():
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_picks_layout_is_a_pure_host_function(oracle):
+    """mlx_picks_levels / mlx_picks_layout need no GPU: level count and offsets of the min/max pyramid
+    (reference app.cpp:352-369) agree with the oracle for every size class."""
+    import ctypes as C
+
+    import numpy as np
+
+    from melonix_b200 import capi
+    L = capi.lib()
+    for n in [0, 1, 2, 3, 4, 5, 7, 8, 9, 4095, 4096, 4097, 14_400_000, 345_600_000, 2**31 - 65537]:
+        levels = L.mlx_picks_levels(n)
+        off = np.zeros(levels + 1, np.int64)
+        total = L.mlx_picks_layout(n, off.ctypes.data_as(C.c_void_p))
+        o = oracle.lib()
+        assert levels == o.mlxo_picks_levels(C.c_int64(n))
+        ooff = np.zeros(levels + 1, np.int64)
+        o.mlxo_picks_layout.restype = C.c_int64
+        assert total == o.mlxo_picks_layout(C.c_int64(n), ooff.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(off, ooff)
+        assert total == sum(n >> (l + 1) for l in range(levels))
