@@ -60,6 +60,17 @@ def main():
                         s_rate=e["schedule"]["rate"], s_out_off=e["schedule"]["out_off"],
                         s_next=e["schedule"]["next"], seconds=3.0)
 
+    # --- waveform min/max pyramid + range queries (App::calcPicks / getMinMaxFromRange, app.cpp:347-426)
+    x = S.vibrato_tone(5003 / 48000.0 + 0.01, seed=31)[:5003]
+    pairs, off = O.picks_build(x)
+    rng = np.random.default_rng(31)
+    start = rng.integers(0, 5000, 300)
+    ranges = np.stack([start, np.minimum(start + (2.0 ** rng.uniform(0, 12, 300)).astype(np.int64), 5002)], 1)
+    ranges = np.concatenate([ranges, [[5, 5], [7, 3], [5003, 5003], [-3, 10], [10, -3], [0, 5003], [0, 5002], [3, 4]]])
+    ranges = ranges.astype(np.int32)
+    np.savez_compressed(OUT / "picks_5003.npz", n=5003, seed=31, pairs=pairs, level_off=off, ranges=ranges,
+                        minmax=O.minmax_ranges(x, pairs, off, ranges))
+
     # --- colour ramp
     v = np.linspace(0, 3.0, 4001).astype(np.float32)
     np.savez_compressed(OUT / "colormap.npz", v=v, k=np.float32(100.0), rgb=O.colormap(v, 100.0))

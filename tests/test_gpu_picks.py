@@ -91,3 +91,13 @@ def test_device_entry_and_cache_invalidation(engine, oracle):
     b = engine.minmax_ranges(0, r)
     ry, ro = oracle.picks_build(y)
     assert np.array_equal(bits(b), bits(oracle.minmax_ranges(y, ry, ro, r))) and not np.array_equal(a, b)
+
+
+def test_golden_fixture(engine):
+    """tests/golden/picks_5003.npz (made by tests/golden/make_golden.py from the oracle)."""
+    g = np.load(Path(__file__).resolve().parent / "golden" / "picks_5003.npz")
+    x = S.vibrato_tone(5003 / 48000.0 + 0.01, seed=int(g["seed"]))[:int(g["n"])]
+    engine.upload_tracks([x])
+    pairs, off = engine.picks_build(0)
+    assert np.array_equal(off, g["level_off"]) and np.array_equal(bits(pairs), bits(g["pairs"]))
+    assert np.array_equal(bits(engine.minmax_ranges(0, g["ranges"])), bits(g["minmax"]))

@@ -180,3 +180,12 @@ def test_picks_oracle_against_brute_force(oracle):
             assert not e[2].any() and not e[3].any() and not e[5].any()
             assert np.array_equal(e[4], [x[10], x[10]])   # start >= end is tested first (app.cpp:382)
             assert np.array_equal(e[6], [x[3], x[3]])
+
+
+def test_golden_picks(oracle):
+    g = np.load(GOLD / "picks_5003.npz")
+    x = S.vibrato_tone(5003 / 48000.0 + 0.01, seed=int(g["seed"]))[:int(g["n"])]
+    pairs, off = oracle.picks_build(x)
+    assert np.array_equal(off, g["level_off"]) and np.array_equal(pairs.view(np.uint32), g["pairs"].view(np.uint32))
+    mm = oracle.minmax_ranges(x, pairs, off, g["ranges"])
+    assert np.array_equal(mm.view(np.uint32), g["minmax"].view(np.uint32))
