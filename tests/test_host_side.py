@@ -21,12 +21,23 @@ def _has_gpu():
         return False
 
 
+SAN = ["-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-g"]
+
+
+def _build_emulation(cmd):
+    """The emulations index std::vectors exactly as the kernels index shared memory, so they are built
+    with ASan + UBSan when the toolchain has them: an out-of-range slot becomes a test failure."""
+    r = subprocess.run(cmd[:1] + SAN + cmd[1:], capture_output=True, text=True)
+    if r.returncode != 0:
+        subprocess.run(cmd, check=True, capture_output=True)
+
+
 def test_device_fft_emulated_on_host(tmp_path):
     """melonix_b200/csrc/fft.cuh compiled by g++ with a sequential thread-group emulation."""
     exe = tmp_path / "fft_emul"
     gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
-    subprocess.run([gxx, "-std=c++17", "-O2", "-x", "c++", str(ROOT / "tests/host/fft_emul.cpp"), "-x", "c",
-                    str(ROOT / "oracle/fft64.c"), "-o", str(exe), "-lm"], check=True, capture_output=True)
+    _build_emulation([gxx, "-std=c++17", "-O2", "-x", "c++", str(ROOT / "tests/host/fft_emul.cpp"), "-x", "c",
+                      str(ROOT / "oracle/fft64.c"), "-o", str(exe), "-lm"])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
 
@@ -42,8 +53,8 @@ def test_spec_frame_steps_emulated_on_host(tmp_path):
         subprocess.run(["gcc", "-O2", "-fopenmp", "-c", str(ROOT / "oracle" / c), "-o", str(o)], check=True,
                        capture_output=True)
         objs.append(str(o))
-    subprocess.run([gxx, "-std=c++17", "-O2", str(ROOT / "tests/host/spec_frame_emul.cpp"), *objs, "-o", str(exe),
-                    "-lm", "-fopenmp"], check=True, capture_output=True)
+    _build_emulation([gxx, "-std=c++17", "-O2", str(ROOT / "tests/host/spec_frame_emul.cpp"), *objs, "-o", str(exe),
+                      "-lm", "-fopenmp"])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
 
@@ -55,8 +66,7 @@ def test_grain_segmentation_bit_logic_emulated_on_host(tmp_path):
     gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
     o = tmp_path / "grain_ref.o"
     subprocess.run(["gcc", "-O2", "-c", str(ROOT / "oracle/grain_ref.c"), "-o", str(o)], check=True, capture_output=True)
-    subprocess.run([gxx, "-std=c++17", "-O2", str(ROOT / "tests/host/grain_seg_emul.cpp"), str(o), "-o", str(exe), "-lm"],
-                   check=True, capture_output=True)
+    _build_emulation([gxx, "-std=c++17", "-O2", str(ROOT / "tests/host/grain_seg_emul.cpp"), str(o), "-o", str(exe), "-lm"])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
 
