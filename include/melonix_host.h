@@ -6,6 +6,7 @@
  *   warp maps            time2Sample / time2PitchBend / sample2Time / duration  app.cpp:1020-1122
  *   export recurrence    App::exportWav + the bookkeeping half of App::process
  *                        reference app.cpp:1194-1207, 294-329
+ *   waveform queries     App::getMinMaxFromRange  reference app.cpp:380-426 (on a GPU-built pyramid)
  * The per-sample resampling loop itself (app.cpp:331-343) and the float->int16 conversion
  * (app.cpp:1209-1212) run on the GPU (mlx_grain_render, include/melonix_gpu.h).
  */
@@ -44,6 +45,14 @@ MLXH_API int mlxh_export_schedule(const float *wav, int64_t n, int sample_rate, 
                                   const int32_t *g_start, const int32_t *g_len, int ngrains, int32_t *s_gstart,
                                   int32_t *s_glen, float *s_rate, int64_t *s_out_off, float *s_next, int cap,
                                   int *tail_zeros);
+
+/* Waveform level-of-detail cache, host half (melonix_b200/host/picks.hpp): the pyramid is built on the
+ * GPU (mlx_picks_build); single range queries -- one per screen column per UI frame in the reference,
+ * App::getMinMaxFromRange app.cpp:380-426 -- are answered on the host from the downloaded pyramid. */
+MLXH_API int mlxh_picks_levels(int64_t n);
+MLXH_API int64_t mlxh_picks_layout(int64_t n, int64_t *level_off /* [levels + 1] */);
+MLXH_API void mlxh_minmax_ranges(const float *wav, int64_t n, const float *pairs /* [total][2] */,
+                                 const int32_t *start_end, int count, float *out /* [count][2] */);
 
 #ifdef __cplusplus
 }

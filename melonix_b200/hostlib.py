@@ -35,6 +35,7 @@ def lib() -> C.CDLL:
         L.mlxh_sample2time.restype = C.c_double
         L.mlxh_duration.restype = C.c_double
         L.mlxh_time2pitchbend.restype = C.c_float
+        L.mlxh_picks_layout.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -101,3 +102,22 @@ def export_wav(engine, track: int, wav: np.ndarray, sr: int, markers):
     s = export_schedule(wav, sr, markers, gs, gl)
     return engine.grain_render(track, s["gstart"], s["glen"], s["rate"], s["out_off"], s["next"],
                                tail_zeros=s["tail_zeros"])
+
+
+def picks_layout(n: int) -> np.ndarray:
+    """level_off[levels + 1] of the min/max pyramid of an n-sample track (reference app.cpp:352-369)."""
+    L = lib().mlxh_picks_levels(C.c_int64(n))
+    off = np.zeros(L + 1, np.int64)
+    lib().mlxh_picks_layout(C.c_int64(n), off.ctypes.data_as(C.c_void_p))
+    return off
+
+
+def minmax_ranges(wav: np.ndarray, pairs: np.ndarray, ranges) -> np.ndarray:
+    """App::getMinMaxFromRange (app.cpp:380-426) on the host, from a pyramid built by Engine.picks_build."""
+    wav = np.ascontiguousarray(wav, np.float32)
+    pairs = np.ascontiguousarray(pairs, np.float32)
+    r = np.ascontiguousarray(ranges, np.int32).reshape(-1, 2)
+    out = np.zeros((r.shape[0], 2), np.float32)
+    lib().mlxh_minmax_ranges(wav.ctypes.data_as(C.c_void_p), C.c_int64(wav.size), pairs.ctypes.data_as(C.c_void_p),
+                             r.ctypes.data_as(C.c_void_p), C.c_int(r.shape[0]), out.ctypes.data_as(C.c_void_p))
+    return out

@@ -79,7 +79,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert [s for s in syms if not hasattr(L, s)] == []
     H = hostlib.lib()
     hs = hostlib.declared_symbols()
-    assert len(hs) == 6 and [s for s in hs if not hasattr(H, s)] == []
+    assert len(hs) == 9 and [s for s in hs if not hasattr(H, s)] == []
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
@@ -153,3 +153,28 @@ def test_picks_layout_is_a_pure_host_function(oracle):
         assert total == o.mlxo_picks_layout(C.c_int64(n), ooff.ctypes.data_as(C.c_void_p))
         assert np.array_equal(off, ooff)
         assert total == sum(n >> (l + 1) for l in range(levels))
+
+
+def test_host_picks_queries_match_oracle(oracle):
+    """melonix::Picks (host/picks.cpp): layout and single range queries on a pyramid, against the oracle's
+    restatement of app.cpp:347-426 -- bit patterns, NaN and signed zeros included."""
+    from melonix_b200 import hostlib as H
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 2, 3, 9, 1000, 4097, 100003):
+        x = rng.standard_normal(n).astype(np.float32)
+        if n > 50:
+            x[::7] = 0.0
+            x[3::7] = -0.0
+            x[5::101] = np.nan
+        pairs, off = oracle.picks_build(x)
+        assert np.array_equal(H.picks_layout(n), off)
+        if n == 0:
+            r = np.array([[0, 0], [0, 1], [-1, 3], [2, 1]], np.int32)
+        else:
+            s = rng.integers(0, max(n - 1, 1), 3000)
+            e = np.minimum(s + (2.0 ** rng.uniform(0, np.log2(max(n, 2)), 3000)).astype(np.int64), n - 1)
+            r = np.concatenate([np.stack([s, e], 1), [[5, 5], [7, 3], [n, n], [-3, 10], [10, -3], [0, n], [0, n - 1]]])
+        r = r.astype(np.int32)
+        got = H.minmax_ranges(x, pairs if pairs.size else np.zeros((1, 2), np.float32), r)
+        exp = oracle.minmax_ranges(x, pairs, off, r)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), n
