@@ -1,6 +1,8 @@
 /* oracle/colormap_ref.c -- TEST INFRASTRUCTURE ONLY (CPU oracle).
  * Restates the colour ramp of SpecCache::populateTex, reference spec-cache.cpp:77-96.
- * Note the integer constants: 255/3 == 85 and 2*255/3 == 170 (int arithmetic in the reference). */
+ * Note the integer constants: 255/3 == 85 and 2*255/3 == 170 (int arithmetic in the reference).
+ * PINNED against the reference itself: spec-cache.cpp compiled unmodified (oracle/_ref/libapp_ref.so,
+ * the GL shim records the texels handed to glTexImage1D) uploads the same bytes (tests/test_oracle.py). */
 #include "oracle.h"
 #include <math.h>
 

@@ -6,8 +6,10 @@
  *   warp maps            sample2Time / time2Sample / duration / time2PitchBend  app.cpp:1020-1122
  *   grain resampler      App::process   app.cpp:294-345
  *   export driver        App::exportWav app.cpp:1194-1215
- * parity unpinned: app.cpp cannot be built here (SDL2, ImGui, FFmpeg, mika314/ser, sdlpp absent)
- * and the reference has no tests; KAT-4 / KAT-5 are the analytic anchors.
+ * PINNED against the reference itself: app.cpp + save-wav.cpp compile unmodified against the no-op
+ * UI / audio / codec headers of oracle/shim_app (oracle/_ref/libapp_ref.so, driver oracle/ref_app.cpp)
+ * and give identical grains, float samples, int16 samples and warp-map values (tests/test_oracle.py);
+ * KAT-4 / KAT-5 are the analytic anchors.  The reference has no tests of its own.
  *
  * The reference memoises the warp maps by int(val*sampleRate) (app.cpp:1058-1060, 1093-1095).
  * In a fresh export every repeated key is hit with a bit-identical argument (cursor + sz/sr is

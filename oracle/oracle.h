@@ -10,14 +10,18 @@
  *                     reference's own spec.cpp compiled unmodified (oracle/_ref, see ref_spec.cpp)
  *                     and against the analytic KAT-1/KAT-2 values.
  *   - mlxo_colormap : restates SpecCache::populateTex colour ramp (reference spec-cache.cpp:77-96).
- *                     parity unpinned (reference needs GL/ImGui to build; no fixtures exist).
+ *                     PINNED: the reference's spec-cache.cpp compiled unmodified (oracle/_ref/
+ *                     libapp_ref.so, GL calls shimmed; the texels given to glTexImage1D are read back)
+ *                     produces the same bytes in all three segments of the ramp.
  *   - mlxo_grain_*  : restates App::preproc grain segmentation (reference app.cpp:156-235),
  *                     App::process (app.cpp:294-345), App::exportWav (app.cpp:1194-1215) and the
- *                     marker warp maps (app.cpp:1020-1122).  parity unpinned (app.cpp needs
- *                     SDL/ImGui/FFmpeg/ser to build; KAT-4/KAT-5 are the analytic anchors).
+ *                     marker warp maps (app.cpp:1020-1122).  PINNED: the reference's app.cpp and
+ *                     save-wav.cpp compiled unmodified against no-op UI / audio / codec headers
+ *                     (oracle/shim_app, driver oracle/ref_app.cpp) give identical grains, float
+ *                     samples (bit patterns), int16 samples and warp-map values (tests/test_oracle.py).
  *   - mlxo_picks_* / mlxo_minmax_ranges : restate App::calcPicks / App::getMinMaxFromRange
- *                     (reference app.cpp:347-426).  parity unpinned (same reason); brute-force
- *                     min/max over aligned ranges is the analytic anchor.
+ *                     (reference app.cpp:347-426).  PINNED the same way (bit patterns, NaN and signed
+ *                     zeros included); brute-force min/max over aligned ranges as a second anchor.
  *   - mlxo_pv_*     : NOT IN REFERENCE.  Double-precision restatement of PV-spec v1 (DESIGN.md,
  *                     from SURVEY.md Appendix A).  parity unpinned by reference: self-consistency
  *                     target only.

@@ -13,6 +13,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _LIB = _HERE / "_build" / "liboracle.so"
 _REF = _HERE / "_ref" / "libspec_ref.so"
+_REF_APP = _HERE / "_ref" / "libapp_ref.so"
 
 REF_SPECTR_SIZE = 32768  # reference spec.cpp:8
 
@@ -247,3 +248,116 @@ def grain_export(wav: np.ndarray, sr: int, markers, g_start=None, g_len=None):
     return dict(pcm=pcm[:ln].copy(), pcm16=pcm16[:ln].copy(),
                 schedule=dict(gstart=sg[:k].copy(), glen=sl[:k].copy(), rate=srate[:k].copy(),
                               out_off=soff[:k].copy(), next=snext[:k].copy()))
+
+
+# ---------------------------------------------------------------- the reference's own App (oracle/_ref)
+def have_ref_app() -> bool:
+    """oracle/_ref/libapp_ref.so: /root/reference/{app,spec-cache,save-wav,spec}.cpp compiled unmodified
+    against the no-op UI / audio / codec headers of oracle/shim_app (driver: oracle/ref_app.cpp)."""
+    return _REF_APP.exists()
+
+
+_ref_app = None
+
+
+def _ref_app_lib():
+    global _ref_app
+    if _ref_app is None:
+        L = C.CDLL(str(_REF_APP))
+        vp = C.c_void_p
+        L.mlxo_ref_app_create.restype = vp
+        L.mlxo_ref_app_create.argtypes = [vp, C.c_longlong, C.c_int, vp, C.c_int]
+        L.mlxo_ref_app_destroy.argtypes = [vp]
+        L.mlxo_ref_app_grains.argtypes = [vp, vp, vp, C.c_int]
+        L.mlxo_ref_app_picks.argtypes = [vp, vp, C.c_longlong, vp]
+        L.mlxo_ref_app_minmax.argtypes = [vp, vp, C.c_int, vp]
+        L.mlxo_ref_app_sample2time.argtypes = [vp, C.c_int]
+        L.mlxo_ref_app_sample2time.restype = C.c_double
+        L.mlxo_ref_app_time2sample.argtypes = [vp, C.c_double]
+        L.mlxo_ref_app_duration.argtypes = [vp]
+        L.mlxo_ref_app_duration.restype = C.c_double
+        L.mlxo_ref_app_time2pitchbend.argtypes = [vp, C.c_double]
+        L.mlxo_ref_app_time2pitchbend.restype = C.c_float
+        L.mlxo_ref_app_export.argtypes = [vp, C.c_char_p]
+        L.mlxo_ref_app_render.argtypes = [vp, vp, C.c_longlong]
+        L.mlxo_ref_app_render.restype = C.c_longlong
+        L.mlxo_ref_app_speccache_column.argtypes = [vp, C.c_float, C.c_int, C.c_double, C.c_double, vp, C.c_int]
+        _ref_app = L
+    return _ref_app
+
+
+class RefApp:
+    """The reference's `App` after `preproc()` on a synthetic track (no UI, no audio device, no decoder)."""
+
+    def __init__(self, wav: np.ndarray, sr: int, markers=()):
+        self._L = _ref_app_lib()
+        self.wav = np.ascontiguousarray(wav, np.float32)
+        arr, nm = _markers(list(markers))
+        self._h = self._L.mlxo_ref_app_create(_ptr(self.wav), self.wav.size, int(sr), C.cast(arr, C.c_void_p), nm)
+
+    def close(self):
+        if self._h:
+            self._L.mlxo_ref_app_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def grains(self):
+        cap = self.wav.size // 700 + 16
+        gs, gl = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        n = self._L.mlxo_ref_app_grains(self._h, _ptr(gs), _ptr(gl), cap)
+        assert n <= cap
+        return gs[:n].copy(), gl[:n].copy()
+
+    def picks(self):
+        cap = self.wav.size + 8
+        pairs = np.zeros((cap, 2), np.float32)
+        off = np.zeros(40, np.int64)
+        L = self._L.mlxo_ref_app_picks(self._h, _ptr(pairs), cap, off.ctypes.data_as(C.c_void_p))
+        return pairs[:int(off[L])].copy(), off[:L + 1].copy()
+
+    def minmax_ranges(self, ranges):
+        r = np.ascontiguousarray(ranges, np.int32).reshape(-1, 2)
+        out = np.zeros((r.shape[0], 2), np.float32)
+        self._L.mlxo_ref_app_minmax(self._h, _ptr(r), r.shape[0], _ptr(out))
+        return out
+
+    def sample2time(self, s):
+        return self._L.mlxo_ref_app_sample2time(self._h, int(s))
+
+    def time2sample(self, t):
+        return self._L.mlxo_ref_app_time2sample(self._h, float(t))
+
+    def duration(self):
+        return self._L.mlxo_ref_app_duration(self._h)
+
+    def time2pitchbend(self, t):
+        return float(self._L.mlxo_ref_app_time2pitchbend(self._h, float(t)))
+
+    def render(self):
+        """float samples of exportWav's process() loop (app.cpp:1201-1207, 294-345)"""
+        pcm = np.zeros(self.wav.size * 5 + 4096, np.float32)
+        n = self._L.mlxo_ref_app_render(self._h, _ptr(pcm), pcm.size)
+        assert n <= pcm.size
+        return pcm[:n].copy()
+
+    def export_wav(self, path) -> np.ndarray:
+        """App::exportWav -> saveWav; returns the int16 samples found in the file.  NOTE: the reference's
+        saveWav patches the data-chunk size with an 8-byte write (save-wav.cpp:42-43), which zeroes the
+        first two samples of the file; callers compare from sample 2 on."""
+        self._L.mlxo_ref_app_export(self._h, str(path).encode())
+        raw = Path(path).read_bytes()
+        assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and raw[36:40] == b"data"
+        return np.frombuffer(raw[44:], np.int16).copy()
+
+    def speccache_column(self, k: float, width: int, range_time: float, t: float) -> np.ndarray:
+        """RGB texels SpecCache::populateTex hands to glTexImage1D for the column at time t."""
+        rgb = np.zeros((REF_SPECTR_SIZE // 2, 3), np.uint8)
+        n = self._L.mlxo_ref_app_speccache_column(self._h, float(k), int(width), float(range_time), float(t),
+                                                  _ptr(rgb), rgb.shape[0])
+        assert n == rgb.shape[0], n
+        return rgb

@@ -3,8 +3,9 @@
  * Restates the waveform min/max pyramid of the reference:
  *   App::calcPicks            reference app.cpp:347-378
  *   App::getMinMaxFromRange   reference app.cpp:380-426
- * parity unpinned: app.cpp cannot be built here (SDL2 / ImGui / FFmpeg absent) and the reference has
- * no tests; the brute-force min/max over aligned ranges is the analytic anchor (tests/test_oracle.py).
+ * PINNED against the reference itself (app.cpp compiled unmodified, oracle/_ref/libapp_ref.so, driver
+ * oracle/ref_app.cpp): identical pyramids and range-query results, bit for bit; the brute-force min/max
+ * over aligned ranges is a second, analytic anchor (tests/test_oracle.py).
  *
  * Level l holds floor(n / 2^(l+1)) pairs (min, max) over samples [i 2^(l+1), (i+1) 2^(l+1)); levels
  * exist while n > 2^(l+1) (app.cpp:352, :365).  The levels are stored back to back; level_off[l] is

@@ -189,3 +189,133 @@ def test_golden_picks(oracle):
     assert np.array_equal(off, g["level_off"]) and np.array_equal(pairs.view(np.uint32), g["pairs"].view(np.uint32))
     mm = oracle.minmax_ranges(x, pairs, off, g["ranges"])
     assert np.array_equal(mm.view(np.uint32), g["minmax"].view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------
+# The oracle against the reference's OWN application code (oracle/_ref/libapp_ref.so: app.cpp,
+# spec-cache.cpp, save-wav.cpp, spec.cpp compiled unmodified; see oracle/ref_app.cpp).
+needs_ref_app = pytest.mark.skipif(not __import__("oracle.oracle", fromlist=["x"]).have_ref_app(),
+                                   reason="oracle/_ref/libapp_ref.so not built (needs /root/reference)")
+
+MARKER_SETS = [
+    [],
+    [(10, 0, 0, 3.0), (-10, 0, 0, 3.0)],                                            # constant +3 st
+    [(10, 0, 0, -3.0), (-10, 0, 0, -3.0)],
+    [(100000, 0, 0.5, 2.0), (200000, 0, -0.3, -1.5), (280000, 0, 0.0, 4.0)],        # time warp + pitch bends
+]
+
+
+def _mk(markers, n):
+    return [(m[0] if m[0] >= 0 else n + m[0], m[1], m[2], m[3]) for m in markers]
+
+
+@needs_ref_app
+@pytest.mark.parametrize("markers", MARKER_SETS)
+def test_grain_path_pinned_by_reference_app(oracle, markers, tmp_path):
+    """App::preproc grains, App::process float output, App::exportWav int16 output and the warp maps of the
+    reference itself equal the oracle's restatements (oracle/grain_ref.c) bit for bit."""
+    x = S.two_tone(6.0)
+    mk = _mk(markers, x.size)
+    with oracle.RefApp(x, 48000, mk) as app:
+        gs, gl = app.grains()
+        os_, ol = oracle.grain_segment(x)
+        assert np.array_equal(gs, os_) and np.array_equal(gl, ol)
+        o = oracle.grain_export(x, 48000, mk)
+        pcm = app.render()
+        assert pcm.size == o["pcm"].size and np.array_equal(pcm.view(np.uint32), o["pcm"].view(np.uint32))
+        pcm16 = app.export_wav(tmp_path / "out.wav")
+        assert pcm16.size == o["pcm16"].size
+        assert np.array_equal(pcm16[2:], o["pcm16"][2:])      # samples 0-1: clobbered by the reference's saveWav
+        assert not pcm16[:2].any()
+        for t in np.linspace(-0.5, 7.0, 301):
+            assert app.time2sample(t) == oracle.time2sample(mk, 48000, float(t))
+            assert np.float32(app.time2pitchbend(t)) == np.float32(oracle.time2pitchbend(mk, 48000, x.size, float(t)))
+        for s_ in range(-100, x.size, 2999):
+            assert app.sample2time(s_) == oracle.sample2time(mk, 48000, s_)
+        assert app.duration() == oracle.sample2time(mk, 48000, x.size - 1)
+
+
+@needs_ref_app
+def test_grain_segmentation_pinned_on_hard_signals(oracle):
+    """look-3 fallback, noise, silence, short clips, -0.0 / NaN: the reference's own loop vs the oracle."""
+    fs = 48000
+    rng = np.random.default_rng(8)
+    t = np.arange(20 * fs) / fs
+    weird = (0.4 * np.sin(2 * np.pi * 440 * t[:5 * fs])).astype(np.float32)
+    weird[::97] = -0.0
+    weird[5::1013] = np.nan
+    cases = [
+        (0.4 * np.sin(2 * np.pi * 9 * t)).astype(np.float32),
+        (0.4 * np.sin(2 * np.pi * 33 * t) + 0.02 * (rng.random(t.size) - 0.5)).astype(np.float32),
+        (rng.random(5 * fs) - 0.5).astype(np.float32),
+        np.zeros(100000, np.float32), np.full(50000, -0.25, np.float32),
+        S.two_tone(1502 / fs)[:1502], S.two_tone(3100 / fs)[:3100], weird,
+    ]
+    for x in cases:
+        with oracle.RefApp(x, fs, []) as app:
+            gs, gl = app.grains()
+        os_, ol = oracle.grain_segment(x)
+        assert np.array_equal(gs, os_) and np.array_equal(gl, ol)
+
+
+@needs_ref_app
+def test_picks_pinned_by_reference_app(oracle):
+    rng = np.random.default_rng(5)
+    for n in (3, 9, 1000, 4097, 288000):
+        x = rng.standard_normal(n).astype(np.float32)
+        if n > 50:
+            x[::7] = 0.0
+            x[3::7] = -0.0
+            x[5::101] = np.nan
+        with oracle.RefApp(x, 48000, []) as app:
+            rp, roff = app.picks()
+            pairs, off = oracle.picks_build(x)
+            assert np.array_equal(roff, off) and np.array_equal(rp.view(np.uint32), pairs.view(np.uint32))
+            s_ = rng.integers(0, max(n - 1, 1), 3000)
+            e_ = np.minimum(s_ + (2.0 ** rng.uniform(0, np.log2(n), 3000)).astype(np.int64), n - 1)
+            r = np.concatenate([np.stack([s_, e_], 1), [[5, 5], [7, 3], [n, n], [-3, 10], [10, -3], [0, n], [0, n - 1]]])
+            r = r.astype(np.int32)
+            assert np.array_equal(app.minmax_ranges(r).view(np.uint32),
+                                  oracle.minmax_ranges(x, pairs, off, r).view(np.uint32))
+
+
+@needs_ref_app
+def test_colour_ramp_pinned_by_reference_speccache(oracle):
+    """SpecCache::populateTex (spec-cache.cpp:52-110) of the reference: the texels it uploads equal
+    mlxo_colormap applied to the oracle spectrum of the same job, byte for byte, in all three segments."""
+    x = S.vibrato_tone(3.0, seed=11)
+    seen = set()
+    with oracle.RefApp(x, 48000, []) as app:
+        for k in (2.0 ** 15, 2.0 ** 13, 2.0 ** 11):
+            for t in (0.5, 1.7, 2.4):
+                width, range_time = 1280, 10.0
+                rgb = app.speccache_column(k, width, range_time, t)
+                key = int(t * width / range_time)                         # spec-cache.cpp:12
+                start, px = key * range_time / width, range_time / width  # spec-cache.cpp:63-64
+                job = np.array([[oracle.time2sample([], 48000, start), oracle.time2sample([], 48000, start + px)]],
+                               np.int32)
+                ref = oracle.colormap(oracle.spec_batch(x, 32768, job), k)[0]
+                assert np.array_equal(rgb, ref)
+                seen |= {"low"} if (ref[..., 1] == 0).any() else set()
+                seen |= {"mid"} if ((ref[..., 1] > 0) & (ref[..., 2] == 0)).any() else set()
+                seen |= {"high"} if (ref[..., 2] > 0).any() else set()
+    assert seen == {"low", "mid", "high"}
+
+
+@needs_ref_app
+def test_golden_fixtures_equal_reference_outputs(oracle, tmp_path):
+    """The committed grain / picks fixtures are what the reference's own code produces."""
+    g = np.load(GOLD / "grain_p3.npz")
+    x = S.two_tone(float(g["seconds"]))
+    mk = [(10, 0.0, 0.0, 3.0), (x.size - 10, 0.0, 0.0, 3.0)]
+    with oracle.RefApp(x, 48000, mk) as app:
+        gs, gl = app.grains()
+        assert np.array_equal(gs, g["g_start"]) and np.array_equal(gl, g["g_len"])
+        assert np.array_equal(app.render().view(np.uint32), g["pcm"].view(np.uint32))
+        assert np.array_equal(app.export_wav(tmp_path / "g.wav")[2:], g["pcm16"][2:])
+    p = np.load(GOLD / "picks_5003.npz")
+    x = S.vibrato_tone(5003 / 48000.0 + 0.01, seed=int(p["seed"]))[:int(p["n"])]
+    with oracle.RefApp(x, 48000, []) as app:
+        rp, roff = app.picks()
+        assert np.array_equal(roff, p["level_off"]) and np.array_equal(rp.view(np.uint32), p["pairs"].view(np.uint32))
+        assert np.array_equal(app.minmax_ranges(p["ranges"]).view(np.uint32), p["minmax"].view(np.uint32))
