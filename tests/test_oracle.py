@@ -319,3 +319,31 @@ def test_golden_fixtures_equal_reference_outputs(oracle, tmp_path):
         rp, roff = app.picks()
         assert np.array_equal(roff, p["level_off"]) and np.array_equal(rp.view(np.uint32), p["pairs"].view(np.uint32))
         assert np.array_equal(app.minmax_ranges(p["ranges"]).view(np.uint32), p["minmax"].view(np.uint32))
+
+
+@needs_ref_app
+def test_random_marker_sets_reference_oracle_and_host_schedule(oracle):
+    """40 random marker sets (time warp dTime in +-0.4 s, pitch bends in +-12 st, 1-6 markers): the
+    reference's own process() loop, the oracle's restatement and the product's host schedule builder
+    (melonix_b200/host/grain_schedule.cpp, which feeds mlx_grain_render) agree exactly."""
+    from melonix_b200 import hostlib as H
+    x = S.two_tone(4.0)
+    gs, gl = oracle.grain_segment(x)
+    hs, hl = H.grain_segment(x)
+    assert np.array_equal(gs, hs) and np.array_equal(gl, hl)
+    rng = np.random.default_rng(2024)
+    for it in range(40):
+        nm = int(rng.integers(1, 7))
+        samples = np.sort(rng.choice(np.arange(2000, x.size - 2000), nm, replace=False))
+        mk = [(int(s_), 0.0, float(np.round(rng.uniform(-0.4, 0.4), 3)), float(np.round(rng.uniform(-12, 12), 2)))
+              for s_ in samples]
+        o = oracle.grain_export(x, 48000, mk, gs, gl)
+        with oracle.RefApp(x, 48000, mk) as app:
+            pcm = app.render()
+        assert pcm.size == o["pcm"].size, (it, mk)
+        assert np.array_equal(pcm.view(np.uint32), o["pcm"].view(np.uint32)), (it, mk)
+        s = H.export_schedule(x, 48000, mk, hs, hl)
+        for k in ("gstart", "glen", "rate", "next"):
+            assert np.array_equal(s[k], o["schedule"][k]), (it, k, mk)
+        assert np.array_equal(s["out_off"][:-1], o["schedule"]["out_off"])
+        assert s["out_off"][-1] + s["tail_zeros"] == o["pcm"].size
