@@ -178,3 +178,42 @@ def test_host_picks_queries_match_oracle(oracle):
         got = H.minmax_ranges(x, pairs if pairs.size else np.zeros((1, 2), np.float32), r)
         exp = oracle.minmax_ranges(x, pairs, off, r)
         assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), n
+
+
+@pytest.mark.skipif(not Path("/root/reference/app.cpp").exists(), reason="needs the reference tree")
+def test_reference_front_end_links_against_the_drop_in_classes(tmp_path):
+    """INTEGRATION.md section 1, executed: a build directory with the reference's front-end sources
+    (app.cpp, app.hpp, marker.hpp, save-wav.*, the dialog headers: symlinks, nothing copied into the repo)
+    and OUR spec.hpp / spec.cpp / spec-cache.hpp / spec-cache.cpp / range.hpp / texture.hpp in place of the
+    reference's.  The reference's app.cpp compiles unmodified against our class surface and links with
+    libmelonix_b200.so (UI / audio / codec headers: the no-op shims of oracle/shim_app).  Without a GPU
+    the resulting program stops where it must: Spec's constructor refuses to run on the CPU."""
+    ref, host = Path("/root/reference"), ROOT / "melonix_b200" / "host"
+    for f in ("app.cpp", "app.hpp", "file-open.hpp", "file-save-as.hpp", "marker.hpp", "save-wav.cpp", "save-wav.hpp"):
+        (tmp_path / f).symlink_to(ref / f)
+    for f in ("spec.hpp", "spec.cpp", "spec-cache.hpp", "spec-cache.cpp", "range.hpp", "texture.hpp"):
+        (tmp_path / f).symlink_to(host / f)
+    (tmp_path / "stubs.cpp").write_text(
+        '#include "app.hpp"\n'
+        "auto FileOpen::draw() -> bool { return false; }\n"
+        "auto FileOpen::getSelectedFile() const -> std::filesystem::path { return {}; }\n"
+        "FileSaveAs::FileSaveAs(std::string name) : dialogName(std::move(name)) { fileName.fill(0); }\n"
+        "auto FileSaveAs::draw() -> bool { return false; }\n"
+        "auto FileSaveAs::getSelectedFile() const -> std::string { return {}; }\n"
+        'int main() { App app; app.openFile("/nonexistent.wav"); return 0; }\n')
+    gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    flags = ["-std=c++20", "-O1", "-I", str(ROOT / "oracle/shim_app"), "-I", str(ROOT / "oracle/shim"),
+             "-I", str(ROOT / "include"), "-I", str(tmp_path)]
+    objs = []
+    for f in ("app.cpp", "spec.cpp", "spec-cache.cpp", "save-wav.cpp", "stubs.cpp"):
+        o = tmp_path / (f + ".o")
+        r = subprocess.run([gxx, *flags, "-c", str(tmp_path / f), "-o", str(o)], capture_output=True, text=True)
+        assert r.returncode == 0, f + "\n" + r.stderr[-3000:]
+        objs.append(str(o))
+    lib = ROOT / "melonix_b200"
+    r = subprocess.run([gxx, "-o", str(tmp_path / "melonix_dropin"), *objs, "-L", str(lib), "-lmelonix_b200",
+                        f"-Wl,-rpath,{lib}", "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    if not _has_gpu():
+        r = subprocess.run([str(tmp_path / "melonix_dropin")], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
