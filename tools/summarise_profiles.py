@@ -19,7 +19,10 @@ for a, b in (("final_bench_n1.json", f"{tag}_bench_n1.json"), ("final_bench_ref.
              ("final_extra.json", f"{tag}_extra.json"), ("final_seg_probe.log", f"{tag}_grain_segment_probe.txt"), ("final_picks_probe.log", f"{tag}_picks_probe.txt"), ("final_grain_probe.log", f"{tag}_grain_render_probe.txt"),
              ("bench_n2.json", f"{tag}_bench_n2.json"), ("cfg4_n2.json", f"{tag}_cfg4_sharded_n2.json")):
     if (src / a).exists():
-        shutil.copy(src / a, prof / b)
+        txt = (src / a).read_text()
+        if a.endswith(".json") and not txt.lstrip().startswith("{"):  # multi-rank runs: keep the JSON line only
+            txt = [ln for ln in txt.splitlines() if ln.startswith("{")][-1] + "\n"
+        (prof / b).write_text(txt)
 
 # ---- launch list
 launches = src / "final_launches_bench.csv"
