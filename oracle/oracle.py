@@ -14,6 +14,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB = _HERE / "_build" / "liboracle.so"
 _REF = _HERE / "_ref" / "libspec_ref.so"
 _REF_APP = _HERE / "_ref" / "libapp_ref.so"
+_DROPIN_APP = _HERE / "_ref" / "libapp_dropin.so"
 
 REF_SPECTR_SIZE = 32768  # reference spec.cpp:8
 
@@ -257,16 +258,22 @@ def have_ref_app() -> bool:
     return _REF_APP.exists()
 
 
-_ref_app = None
+def have_dropin_app() -> bool:
+    """oracle/_ref/libapp_dropin.so: the reference's front-end (app.cpp, save-wav.cpp, unmodified) built on
+    the PRODUCT's Spec / SpecCache (melonix_b200/host) and libmelonix_b200.so -- INTEGRATION.md section 1."""
+    return _DROPIN_APP.exists()
 
 
-def _ref_app_lib():
-    global _ref_app
-    if _ref_app is None:
-        L = C.CDLL(str(_REF_APP))
+_ref_app = {}
+
+
+def _ref_app_lib(which: str = "ref"):
+    if which not in _ref_app:
+        L = C.CDLL(str(_REF_APP if which == "ref" else _DROPIN_APP))
         vp = C.c_void_p
         L.mlxo_ref_app_create.restype = vp
         L.mlxo_ref_app_create.argtypes = [vp, C.c_longlong, C.c_int, vp, C.c_int]
+        L.mlxo_ref_app_last_error.restype = C.c_char_p
         L.mlxo_ref_app_destroy.argtypes = [vp]
         L.mlxo_ref_app_grains.argtypes = [vp, vp, vp, C.c_int]
         L.mlxo_ref_app_picks.argtypes = [vp, vp, C.c_longlong, vp]
@@ -282,18 +289,22 @@ def _ref_app_lib():
         L.mlxo_ref_app_render.argtypes = [vp, vp, C.c_longlong]
         L.mlxo_ref_app_render.restype = C.c_longlong
         L.mlxo_ref_app_speccache_column.argtypes = [vp, C.c_float, C.c_int, C.c_double, C.c_double, vp, C.c_int]
-        _ref_app = L
-    return _ref_app
+        _ref_app[which] = L
+    return _ref_app[which]
 
 
 class RefApp:
     """The reference's `App` after `preproc()` on a synthetic track (no UI, no audio device, no decoder)."""
 
-    def __init__(self, wav: np.ndarray, sr: int, markers=()):
-        self._L = _ref_app_lib()
+    def __init__(self, wav: np.ndarray, sr: int, markers=(), build: str = "ref"):
+        """build = "ref": everything is the reference's code (CPU).  build = "dropin": the reference's
+        front-end on the product's Spec / SpecCache (needs a B200)."""
+        self._L = _ref_app_lib(build)
         self.wav = np.ascontiguousarray(wav, np.float32)
         arr, nm = _markers(list(markers))
         self._h = self._L.mlxo_ref_app_create(_ptr(self.wav), self.wav.size, int(sr), C.cast(arr, C.c_void_p), nm)
+        if not self._h:
+            raise RuntimeError(self._L.mlxo_ref_app_last_error().decode(errors="replace"))
 
     def close(self):
         if self._h:

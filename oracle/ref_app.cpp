@@ -59,6 +59,9 @@ extern "C" {
 
 /* A fresh App holding `wav` at `sampleRate` with `markers` (sorted by sample), after App::preproc():
  * grains, picks and the Spec are built by the reference's own code. */
+static std::string g_last_error;
+const char *mlxo_ref_app_last_error() { return g_last_error.c_str(); }
+
 void *mlxo_ref_app_create(const float *wav, long long n, int sampleRate, const mlxo_ref_marker *m, int nm) {
   auto *a = new App();
   a->wavData.assign(wav, wav + n);
@@ -71,7 +74,13 @@ void *mlxo_ref_app_create(const float *wav, long long n, int sampleRate, const m
     mk.pitchBend = m[i].pitchBend;
     a->markers.push_back(mk);
   }
-  a->preproc();
+  try {
+    a->preproc();
+  } catch (const std::exception &e) { /* only the drop-in build can throw: its Spec needs a B200 */
+    g_last_error = e.what();
+    delete a;
+    return nullptr;
+  }
   return a;
 }
 

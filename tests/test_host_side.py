@@ -217,3 +217,18 @@ def test_reference_front_end_links_against_the_drop_in_classes(tmp_path):
     if not _has_gpu():
         r = subprocess.run([str(tmp_path / "melonix_dropin")], capture_output=True, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_drop_in_build_refuses_to_run_without_a_gpu(oracle):
+    """oracle/_ref/libapp_dropin.so (reference front-end + product Spec/SpecCache, oracle/Makefile `dropin`)
+    loads next to the all-reference build and, without a B200, fails loudly in Spec's constructor."""
+    if not oracle.have_dropin_app():
+        pytest.skip("oracle/_ref/libapp_dropin.so not built (needs /root/reference)")
+    if _has_gpu():
+        pytest.skip("checks the no-GPU failure mode")
+    x = S.two_tone(1.0)
+    with oracle.RefApp(x, 48000, []) as ref:
+        assert ref.grains()[0].size > 0
+    with pytest.raises(RuntimeError) as e:
+        oracle.RefApp(x, 48000, [], build="dropin")
+    assert "no CPU fallback" in str(e.value)
