@@ -28,6 +28,7 @@
 
 #include "fft.cuh"
 #include "kernels.h"
+#include "pv_shift.cuh"
 #include "tma.cuh"
 
 #ifndef MLX_UNROLL_PAIR
@@ -89,13 +90,6 @@ struct PvG {
   static constexpr int value = 8192 / N;    // K_S
   static constexpr int ka_ctas = (N <= MLX_KA_CTAS_MAXN) ? MLX_KA_CTAS : 1;  // (two 8192-point CTAs do not fit one SM)
   static constexpr int analyze = (16384 / ka_ctas) / N;           // K_A
-};
-
-// what the pair phase leaves for the gather phase, stored in the first 8 bytes of the bin's (dead)
-// FFT slot: |X| with the cut-flip flag in its sign bit, and the wrapped phase advance in 2^-32 turns
-struct MagD {
-  float mag;
-  int d;
 };
 
 template <int TPF>
@@ -254,44 +248,12 @@ __device__ __forceinline__ float shift_one_bin(const cplx<double>* zb, int j, ui
   return smag;
 }
 
-// Frame-invariant part of the bin shift of one output bin j at a constant rate (MLX_GATHER_V2).
-// With K_j = [klo, khi], kh = khi and d' the signed phase advance (d32, -+2^32 on a cut flip)
-//     inc = (r_fix * (kh * 2^30 + d') + 2^25) >> 26   (mod 2^32)
-// is a product in the ring of integers mod 2^64, so the kh term is added once per launch:
-//     base = r_fix * kh * 2^30 + 2^25,   inc = (base + r_eff * d') >> 26.
-// An empty K_j (s_nu = j, inc = frac(j / 4) * 2^32, smag = 0) is the same formula with
-// base = (j & 3) << 56 (+ 2^25, which the shift drops) reading an all-zero (mag, d) record.  The
-// result is bit-identical to shift_one_bin(); the per-frame work is one 32 x 32 + 64 multiply-add,
-// the flip term and the shift.
-struct ShiftConst {
-  uint32_t slot;  // padded index of bin kh's (mag, d) record inside a frame buffer, or the zero record
-  unsigned long long base;
-};
-__device__ __forceinline__ ShiftConst make_shift_const(int j, uint32_t kk, uint32_t r_fix, int zero_slot) {
-  const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
-  ShiftConst c;
-  if (klo <= khi) {
-    c.slot = (uint32_t)fft_pad(khi);
-    c.base = (unsigned long long)r_fix * ((unsigned long long)khi << 30) + (1ULL << 25);
-  } else {  // reads (mag, d) = (0, 0): smag = 0 and the product term vanishes
-    c.slot = (uint32_t)zero_slot;
-    c.base = ((unsigned long long)((uint32_t)j & 3u) << 56) + (1ULL << 25);
-  }
-  return c;
-}
-// one frame of one output bin whose K_j has at most one element (rate >= 1)
+// one frame of one output bin whose K_j has at most one element (rate >= 1); constants: pv_shift.cuh
 __device__ __forceinline__ float shift_one_bin_v2(const cplx<double>* zb, const ShiftConst& c, int r_fix,
                                                   uint32_t& inc) {
   const MagD mh = *reinterpret_cast<const MagD*>(zb + c.slot);
   const uint32_t mb = __float_as_uint(mh.mag);
-  // cut flip (sign bit of the stored magnitude): d' = d32 + 2^32 when d32 < 0, d32 - 2^32 otherwise
-  const int hi_adj = ((int)mb >> 31) & (mh.d < 0 ? r_fix : -r_fix);
-  // base + d * r_fix as ONE signed 32 x 32 + 64 multiply-add (the compiler expands the C expression
-  // into a 64 x 64 product), the flip term goes into the high word, the shift is a funnel shift
-  unsigned long long prod;
-  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(prod) : "r"(mh.d), "r"(r_fix), "l"(c.base));
-  const uint32_t lo = (uint32_t)prod, hi = (uint32_t)(prod >> 32) + (uint32_t)hi_adj;
-  inc = __funnelshift_r(lo, hi, 26);
+  inc = shift_inc(c.base, mh.d, mb, r_fix);
   return __uint_as_float(mb & 0x7fffffffu);
 }
 

@@ -71,6 +71,17 @@ def test_grain_segmentation_bit_logic_emulated_on_host(tmp_path):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
 
 
+def test_bin_shift_ring_arithmetic_on_host(tmp_path):
+    """pv_shift.cuh (the phase-increment arithmetic of the analysis kernel, compiled here by g++): 4.4 M
+    cases incl. INT_MIN advances, cut flips and empty K_j against a 128-bit evaluation of the defining
+    formula (exact) and against the spec's double formula (within the one rounding both perform)."""
+    exe = tmp_path / "pv_shift_emul"
+    gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    _build_emulation([gxx, "-std=c++17", "-O2", str(ROOT / "tests/host/pv_shift_emul.cpp"), "-o", str(exe), "-lm"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
+
+
 def test_c_abi_exports_every_declared_symbol():
     from melonix_b200 import capi, hostlib
     L = capi.lib()
