@@ -5,6 +5,8 @@ mkdir -p gpurun_out
 o=gpurun_out
 ( time python -m pytest tests -m gpu -x -q ) > $o/final_pytest.log 2>&1; tail -4 $o/final_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > $o/final_smoke.log 2>&1; tail -2 $o/final_smoke.log
+# opt-in: the reference's own front-end on the product's GPU Spec / SpecCache (oracle/_ref/libapp_dropin.so)
+MLX_RUN_DROPIN_GPU=1 python -m pytest tests/test_zz_dropin_gpu.py -m gpu -q > $o/final_dropin.log 2>&1; tail -3 $o/final_dropin.log
 python bench.py --impl reference > $o/final_bench_ref.json 2> $o/final_bench_ref.err
 python bench.py > $o/final_bench_n1.json 2> $o/final_bench_n1.err; tail -c 600 $o/final_bench_n1.json
 python tools/extra_bench.py > $o/final_extra.json 2> $o/final_extra.err
