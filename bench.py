@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = all this process may use)")
     return ap.parse_args()
 
 
@@ -77,12 +78,33 @@ def vibrato_track_numpy(seconds, seed, f_base=220.0):
 
 
 # ------------------------------------------------------------------------------------------------
+def host_cores():
+    """Host threads this process may use.  Taken from the scheduler affinity, NOT from OpenMP:
+    torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, which would silently turn the
+    "all host cores" CPU arm into a single-core run (round-1 SCALE artefact)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_one_thread(sec=10.0):
+    """The same port on ONE thread (the reference's actual concurrency: one worker, spec.cpp:11)."""
+    from oracle import oracle as O
+    x = vibrato_track_numpy(sec, 1234)[None, :]
+    r = semitone_ratio(SEMITONES)
+    F = O.pv_num_frames(x.shape[1], HOP)
+    t0 = time.perf_counter()
+    O.pv_run_batch(x, FFT_N, HOP, r, FS, 1)
+    return F / (time.perf_counter() - t0)
+
+
 def cpu_baseline(target_seconds, nthreads=0):
     """Times the oracle port of the path (oracle/pv_ref.c, OpenMP over tracks) on the host cores.
     Sample: `threads` tracks x 20 s of the cfg-3 signal, repeated until ~target_seconds elapse."""
     from oracle import oracle as O
     O.build()
-    threads = nthreads or O.num_threads()
+    threads = nthreads or host_cores()
     sec = 20.0
     base = vibrato_track_numpy(sec, 1234)
     x = np.ascontiguousarray(np.tile(base, (threads, 1)))
@@ -97,6 +119,7 @@ def cpu_baseline(target_seconds, nthreads=0):
         if el >= target_seconds or reps >= 50:
             break
     return dict(value=threads * F * reps / el, unit="frames/s", cores=threads, kind="port",
+                one_thread_value=cpu_one_thread(),
                 sample=f"{threads} tracks x {sec:.0f} s (cfg-3 signal, {F} frames each), {reps} passes, "
                        f"{el:.1f} s wall; double-precision oracle/pv_ref.c, OpenMP over tracks "
                        f"(FFT engine: in-repo radix-4 double FFT, not FFTW)")
@@ -111,7 +134,7 @@ def reference_arm(args):
         return
     from oracle import oracle as O
     O.build()
-    threads = O.num_threads()
+    threads = args.cpu_threads or host_cores()   # explicit: never inherit OMP_NUM_THREADS=1 from torchrun
     sec = 20.0
     base = vibrato_track_numpy(sec, 1234)
     x = np.ascontiguousarray(np.tile(base, (threads, 1)))
@@ -132,7 +155,8 @@ def reference_arm(args):
                 dtype="f64", data="synthetic", impl="reference",
                 config=dict(workload="cfg-3 signal, 2048-FFT/512-hop, +3 st, bounded CPU sample", fft=FFT_N, hop=HOP,
                             semitones=SEMITONES, tracks=threads, seconds=sec),
-                cpu_baseline=dict(value=v, unit="frames/s", cores=threads, kind="port", sample=sample),
+                cpu_baseline=dict(value=v, unit="frames/s", cores=threads, kind="port", sample=sample,
+                                  one_thread_value=cpu_one_thread(), omp_num_threads_env=os.environ.get("OMP_NUM_THREADS")),
                 e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -358,7 +382,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args.cpu_seconds)
+        cpu = cpu_baseline(args.cpu_seconds, args.cpu_threads)
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps,

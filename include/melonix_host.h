@@ -54,6 +54,11 @@ MLXH_API int64_t mlxh_picks_layout(int64_t n, int64_t *level_off /* [levels + 1]
 MLXH_API void mlxh_minmax_ranges(const float *wav, int64_t n, const float *pairs /* [total][2] */,
                                  const int32_t *start_end, int count, float *out /* [count][2] */);
 
+/* The colour ramp of SpecCache::populateTex (reference spec-cache.cpp:77-96) on the host: rgb =
+ * [count][3].  New columns are coloured by the fused GPU epilogue (mlx_spec_batch_rgb); the drop-in
+ * Spec uses this only to recolour a column whose floats are cached when the brightness changes. */
+MLXH_API void mlxh_colour_ramp(const float *mag, int count, float k, uint8_t *rgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,6 +317,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     float* cur = tile + (bi & 1) * TILE;
     // ---- TMA: prefetch the next batch's tile, then wait for this one
     if (tid == 0 && bi + 1 < nbatch) {
+      fence_proxy_async();  // the tile's generic-proxy reads (two batches ago, ordered by __syncthreads) before its refill
       mbar_expect_tx(mbar + ((bi + 1) & 1), TILE * sizeof(float));
       tma_load_1d(tile + ((bi + 1) & 1) * TILE, tr.x + (f_first + G - 3) * H, TILE * sizeof(float),
                   mbar + ((bi + 1) & 1));

@@ -277,6 +277,7 @@ spec_frames_kernel(const SpecArgs a, const int fpc) {
     }
     __syncthreads();  // every group has taken its samples out of tile (b & 1); previous epilogue reads done
     if (tid == 0 && b + 2 < nbatch) {
+      fence_proxy_async();  // generic-proxy reads of the tile (ordered by the barrier) before the async-proxy refill
       mbar_expect_tx(mbar + (b & 1), tile_bytes);
       tma_load_1d(tile + (b & 1) * span, src0 + (long long)(b + 2) * JPB * hop, tile_bytes, mbar + (b & 1));
     }

@@ -17,6 +17,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// Orders earlier generic-proxy accesses of shared memory (ordinary ld/st.shared, made visible to this
+// thread by a barrier) before later async-proxy accesses (the bulk copy that overwrites the buffer).
+// The PTX memory model requires it between "everybody has read the tile" and "TMA refills the tile".
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // dst, src and bytes must be multiples of 16.
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -32,7 +32,7 @@ class Engine:
         check(self._L.mlx_create(C.byref(h), int(device)))
         self._h = h
         self.device = int(device)
-        self._keep = []  # arrays that must outlive asynchronous launches
+        self._keep = []  # pointer arrays of the call being issued (the C call reads them before it returns)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -119,6 +119,7 @@ class Engine:
     # ------------------------------------------------------------------ PV path
     def _params(self, fftN, hop, rate, sample_rate, frame_begin=-1, frame_end=-1, wave_mib=0,
                 phase_in=None, rate_per_frame=None) -> PvParams:
+        self._keep.clear()  # the previous call has returned: its host pointer arrays were consumed
         p = PvParams()
         p.fftN, p.hop, p.rate, p.sample_rate = int(fftN), int(hop), float(rate), float(sample_rate)
         p.frame_begin, p.frame_end, p.wave_mib = int(frame_begin), int(frame_end), int(wave_mib)

@@ -2,6 +2,7 @@
 // -DMELONIX_HEADLESS; runs on the GPU box).  tests/test_host_cpp_gpu.py feeds it raw files and
 // compares what it writes with the oracle.
 //   host_test spec      wav.f32 jobs.i32 out.f32        Spec::getSpec for every job (async contract checked)
+//   host_test recolour  wav.f32 jobs.i32 k out.u8       getSpec, then getSpecRgb(k): served at once from the cached floats
 //   host_test speccache wav.f32 k width rangeTime out.u8   SpecCache::getTex for every column
 //   host_test export    wav.f32 sampleRate semitones out.i16   segment -> schedule -> mlx_grain_render
 #include "grain_schedule.hpp"
@@ -81,6 +82,41 @@ static int runSpec(char **a)
   return remaining == 0 ? 0 : 4;
 }
 
+// Brightness change on warm columns: once getSpec has delivered the floats, getSpecRgb must answer on
+// its first call (host colour ramp on the cached floats, as the reference's populateTex does) instead
+// of going back to the GPU and returning {} meanwhile.
+static int runRecolour(char **a)
+{
+  auto wav = readAll<float>(a[0]);
+  const auto jobs = readAll<int32_t>(a[1]);
+  const float k = static_cast<float>(std::atof(a[2]));
+  const int count = static_cast<int>(jobs.size() / 2);
+  const int half = Spec::spectrSize() / 2;
+  Spec spec(std::span<float>{wav.data(), wav.size()});
+  int remaining = count;
+  for (int spin = 0; remaining > 0 && spin < 20000; ++spin)
+  {
+    remaining = 0;
+    for (int j = 0; j < count; ++j)
+      remaining += spec.getSpec(jobs[2 * j], jobs[2 * j + 1]).empty();
+    if (remaining)
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
+  std::vector<unsigned char> out(static_cast<size_t>(count) * half * 3);
+  int immediate = 0;
+  for (int j = 0; j < count && remaining == 0; ++j)
+  {
+    const auto rgb = spec.getSpecRgb(jobs[2 * j], jobs[2 * j + 1], k);
+    if (static_cast<int>(rgb.size()) != half)
+      continue;
+    ++immediate;
+    std::memcpy(out.data() + static_cast<size_t>(j) * half * 3, rgb.data(), static_cast<size_t>(half) * 3);
+  }
+  writeAll(a[3], out.data(), out.size());
+  std::printf("recolour: jobs=%d not_ready=%d immediate=%d half=%d\n", count, remaining, immediate, half);
+  return (remaining == 0 && immediate == count) ? 0 : 4;
+}
+
 static int runSpecCache(char **a)
 {
   auto wav = readAll<float>(a[0]);
@@ -151,10 +187,12 @@ int main(int argc, char **argv)
 {
   if (argc >= 5 && !std::strcmp(argv[1], "spec"))
     return runSpec(argv + 2);
+  if (argc >= 6 && !std::strcmp(argv[1], "recolour"))
+    return runRecolour(argv + 2);
   if (argc >= 7 && !std::strcmp(argv[1], "speccache"))
     return runSpecCache(argv + 2);
   if (argc >= 6 && !std::strcmp(argv[1], "export"))
     return runExport(argv + 2);
-  std::fprintf(stderr, "usage: host_test spec|speccache|export ...\n");
+  std::fprintf(stderr, "usage: host_test spec|recolour|speccache|export ...\n");
   return 1;
 }

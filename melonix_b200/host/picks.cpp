@@ -1,6 +1,8 @@
 // melonix_b200/host/picks.cpp -- see picks.hpp / include/melonix_host.h.
 #include "picks.hpp"
 
+#include "colour_ramp.hpp"
+
 #include "../../include/melonix_host.h"
 
 #include <algorithm>
@@ -103,6 +105,14 @@ void mlxh_minmax_ranges(const float *wav, int64_t n, const float *pairs, const i
     const auto mm = picks.getMinMaxFromRange(start_end[2 * i], start_end[2 * i + 1]);
     out[2 * i] = mm.first;
     out[2 * i + 1] = mm.second;
+  }
+}
+void mlxh_colour_ramp(const float *mag, int count, float k, uint8_t *rgb)
+{
+  for (int i = 0; i < count; ++i)
+  {
+    const auto t = melonix::rampTexel(mag[i], k);
+    std::copy(t.begin(), t.end(), rgb + 3 * static_cast<size_t>(i));
   }
 }
 }

@@ -47,7 +47,9 @@ private:
     std::vector<float> spec;
     std::vector<Rgb> rgb;
     float rgbGain = 0.f;
-    bool wantRgb = false;
+    bool wantRgb = false;  // SpecCache asked for texels at rgbGain
+    bool wantSpec = false; // somebody asked for the float magnitudes (getSpec)
+    bool pending = false;  // queued or being computed by the worker
     std::list<Range>::iterator age;
   };
 

@@ -121,3 +121,13 @@ def minmax_ranges(wav: np.ndarray, pairs: np.ndarray, ranges) -> np.ndarray:
     lib().mlxh_minmax_ranges(wav.ctypes.data_as(C.c_void_p), C.c_int64(wav.size), pairs.ctypes.data_as(C.c_void_p),
                              r.ctypes.data_as(C.c_void_p), C.c_int(r.shape[0]), out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def colour_ramp(mag: np.ndarray, k: float) -> np.ndarray:
+    """SpecCache::populateTex's colour ramp (reference spec-cache.cpp:77-96) on the host: [..., 3] uint8.
+    The drop-in Spec recolours cached float columns with it when the brightness gain changes."""
+    mag = np.ascontiguousarray(mag, np.float32)
+    out = np.zeros(mag.shape + (3,), np.uint8)
+    lib().mlxh_colour_ramp(mag.ctypes.data_as(C.c_void_p), C.c_int(mag.size), C.c_float(k),
+                           out.ctypes.data_as(C.c_void_p))
+    return out

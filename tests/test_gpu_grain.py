@@ -99,6 +99,24 @@ def test_cpp_speccache_textures(tmp_path, oracle):
     assert d.max() <= 1 and (d > 0).mean() < 1e-3
 
 
+def test_cpp_spec_recolours_cached_columns_at_once(tmp_path, oracle):
+    """Brightness change on warm columns (ADVICE r1): with the floats cached, Spec::getSpecRgb answers on
+    its first call with the host colour ramp -- byte-identical to the reference's populateTex arithmetic
+    on those floats -- instead of relaunching and returning {} (a black flash) meanwhile."""
+    x = S.vibrato_tone(0.5, seed=12)
+    jobs = S.regular_jobs(x.size, 375)[:40]
+    x.tofile(tmp_path / "wav.f32")
+    jobs.tofile(tmp_path / "jobs.i32")
+    k = 2.0 ** 12
+    out = _host_test("recolour", tmp_path / "wav.f32", tmp_path / "jobs.i32", k, tmp_path / "out.u8",
+                     env={"MELONIX_SPECTR_SIZE": "4096"})
+    assert "not_ready=0" in out and "immediate=40" in out
+    got = np.fromfile(tmp_path / "out.u8", np.uint8).reshape(40, 2048, 3).astype(np.int32)
+    ref = oracle.colormap(oracle.spec_batch(x, 4096, jobs), k).astype(np.int32)
+    d = np.abs(got - ref)
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3   # FP32 magnitudes on the GPU vs double in the oracle
+
+
 def test_cpp_export_path(tmp_path, oracle):
     x = S.two_tone(5.0)
     x.tofile(tmp_path / "wav.f32")

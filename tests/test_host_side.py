@@ -103,7 +103,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert [s for s in syms if not hasattr(L, s)] == []
     H = hostlib.lib()
     hs = hostlib.declared_symbols()
-    assert len(hs) == 9 and [s for s in hs if not hasattr(H, s)] == []
+    assert len(hs) == 10 and [s for s in hs if not hasattr(H, s)] == []
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
@@ -215,7 +215,7 @@ def test_reference_front_end_links_against_the_drop_in_classes(tmp_path):
     ref, host = Path("/root/reference"), ROOT / "melonix_b200" / "host"
     for f in ("app.cpp", "app.hpp", "file-open.hpp", "file-save-as.hpp", "marker.hpp", "save-wav.cpp", "save-wav.hpp"):
         (tmp_path / f).symlink_to(ref / f)
-    for f in ("spec.hpp", "spec.cpp", "spec-cache.hpp", "spec-cache.cpp", "range.hpp", "texture.hpp"):
+    for f in ("spec.hpp", "spec.cpp", "spec-cache.hpp", "spec-cache.cpp", "range.hpp", "texture.hpp", "colour_ramp.hpp"):
         (tmp_path / f).symlink_to(host / f)
     (tmp_path / "stubs.cpp").write_text(
         '#include "app.hpp"\n'
@@ -256,3 +256,16 @@ def test_drop_in_build_refuses_to_run_without_a_gpu(oracle):
     with pytest.raises(RuntimeError) as e:
         oracle.RefApp(x, 48000, [], build="dropin")
     assert "no CPU fallback" in str(e.value)
+
+
+def test_host_colour_ramp_equals_reference_ramp(oracle):
+    """mlxh_colour_ramp (what the drop-in Spec recolours cached columns with on a brightness change)
+    against the oracle's ramp, which is pinned byte for byte to the reference's populateTex
+    (tests/test_oracle.py): all three segments, the thresholds, clamping, negative and NaN-free input."""
+    from melonix_b200 import hostlib as H
+    rng = np.random.default_rng(5)
+    for k in (2.0 ** 15, 2.0 ** 11, 700.0, 1.0):
+        v = np.concatenate([rng.random(20000).astype(np.float32) * np.float32(300.0 / k),
+                            np.array([0, 84.999, 85, 85.001, 169.999, 170, 170.001, 254.999, 255, 256, -1], np.float32)
+                            / np.float32(k)])
+        assert np.array_equal(H.colour_ramp(v, k), oracle.colormap(v, float(k)))
