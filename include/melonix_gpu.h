@@ -123,11 +123,64 @@ MLX_API int mlx_pv_run_dev(mlx_ctx *ctx, const mlx_pv_params *p, float *const *o
  * by time range -- plus peak / f0. */
 MLX_API int mlx_pv_phase_totals_dev(mlx_ctx *ctx, const mlx_pv_params *p, uint32_t *const *totals_dev,
                             int32_t *const *out_peak_dev, float *const *out_f0_dev);
+/* Split form of mlx_pv_run_dev, for callers that need the phase totals BEFORE synthesis (time-range
+ * sharding: analyse once, exchange the totals, synthesise with the carried-in phase).
+ * mlx_pv_analyze_dev runs the analysis (K_A) over [frame_begin, frame_end) exactly once, leaves the
+ * shifted magnitudes and chunk-local phase sums staged in device memory (one wave: 8*(fftN/2+32) bytes
+ * per frame and track), and writes the per-track phase totals of the owned frames (fftN/2+1 uint32,
+ * device) plus peak / f0.  mlx_pv_synth_dev then applies p->phase_in_dev to the staged analysis (a
+ * microsecond rescan of the chunk totals) and synthesises the owned hops.  Same p (geometry, rate,
+ * frame range) in both calls; any upload or other PV call in between invalidates the staged analysis
+ * (MLX_ERR_STATE).  analyze + synth is bit-identical to mlx_pv_run_dev with the same phase_in_dev. */
+MLX_API int mlx_pv_analyze_dev(mlx_ctx *ctx, const mlx_pv_params *p, uint32_t *const *totals_dev,
+                               int32_t *const *out_peak_dev, float *const *out_f0_dev);
+MLX_API int mlx_pv_synth_dev(mlx_ctx *ctx, const mlx_pv_params *p, float *const *out_wav_dev);
 /* End-to-end convenience for host buffers: uploads `wav`, runs, downloads, with the copies of
  * track t+1 / t-1 overlapped with the kernels of track t on separate streams. */
 MLX_API int mlx_pv_process_host(mlx_ctx *ctx, const mlx_pv_params *p, const float *const *wav,
                         const int64_t *n, int ntracks, float *const *out_wav,
                         int32_t *const *out_peak, float *const *out_f0);
+
+/* ---- one long file across the GPUs of a node: time-range sharding (BASELINE configs[3]) ---------
+ * One rank (process or host thread) per GPU, each with its own mlx_ctx.  Rank r owns frames
+ * [F*r/G, F*(r+1)/G) -- frame convention of reference spec.cpp:47 / spec-cache.cpp:63-65 -- and the
+ * output hops of those frames.  The communicator wraps NCCL (bound at run time with
+ * dlopen("libnccl.so.2"); MLX_NCCL_LIB overrides the name): rank 0 obtains 128 opaque bytes from
+ * mlx_comm_unique_id, the caller distributes them (any transport), every rank calls mlx_comm_create. */
+typedef struct mlx_comm mlx_comm;
+typedef struct {
+  int64_t frame_begin, frame_end; /* owned frames (global indices)                                   */
+  int64_t own_lo, own_hi;         /* owned samples = output hops of the owned frames                  */
+  int64_t need_lo, need_hi;       /* samples the rank must hold: owned + both seam overlaps           */
+  int64_t frame_offset;           /* local frame index = global frame index - frame_offset            */
+} mlx_time_shard;
+/* Pure host function: the shard of `rank`.  Left overlap = fftN samples + the halo frame's hop (the
+ * frame before the first owned one seeds the phase difference), right overlap = 3 hops (the tails of
+ * the next three frames overlap-add into the owned hops); both clipped to [0, n). */
+MLX_API int mlx_shard_frames(int64_t n, int fftN, int hop, int world, int rank, mlx_time_shard *out);
+MLX_API int mlx_comm_unique_id(void *id128);
+MLX_API int mlx_comm_create(mlx_comm **out, mlx_ctx *ctx, const void *id128, int world, int rank);
+MLX_API void mlx_comm_destroy(mlx_comm *comm);
+MLX_API int mlx_comm_info(const mlx_comm *comm, int *world, int *rank, int *nccl_version);
+/* Phase-vocodes `ntracks` mono tracks of n_total samples each (the planar channels of one file) across
+ * the ranks of `comm`.  own_dev[t]: this rank's owned samples [own_lo, own_hi) of track t (device).
+ * Per call and rank: ONE NCCL group of send/recv of the overlap-region samples with the two
+ * neighbours (received straight into the track buffer while the owned samples are copied in), ONE
+ * analysis pass, ONE all-gather of the uint32 phase totals, synthesis of the owned hops.  Outputs
+ * (device, entries or arrays may be NULL): out_own_dev[t] = own_hi-own_lo floats, peak_own_dev[t] /
+ * f0_own_dev[t] = frame_end-frame_begin values.  Bit-identical to the unsharded mlx_pv_run_dev.
+ * Collective: every rank of the communicator must call it with the same p, ntracks and n_total. */
+MLX_API int mlx_pv_run_sharded_dev(mlx_ctx *ctx, mlx_comm *comm, const mlx_pv_params *p,
+                                   const float *const *own_dev, int ntracks, int64_t n_total,
+                                   float *const *out_own_dev, int32_t *const *peak_own_dev,
+                                   float *const *f0_own_dev);
+
+/* The same with host pointers (own[t], out_own[t]: own_hi-own_lo floats; peak_own[t] / f0_own[t]:
+ * frame_end-frame_begin values): upload, run, download; returns when the results are in place.  This is
+ * the call a C++ host makes, one thread (or process) per GPU. */
+MLX_API int mlx_pv_run_sharded(mlx_ctx *ctx, mlx_comm *comm, const mlx_pv_params *p, const float *const *own,
+                               int ntracks, int64_t n_total, float *const *out_own, int32_t *const *peak_own,
+                               float *const *f0_own);
 
 /* ---- grain path (replaces the inner loop of App::process, reference app.cpp:331-343, and the
  *      float->int16 conversion of App::exportWav, app.cpp:1209-1212) ---------------------------- */

@@ -40,6 +40,11 @@ class PvParams(C.Structure):
     ]
 
 
+class TimeShardC(C.Structure):
+    _fields_ = [("frame_begin", C.c_int64), ("frame_end", C.c_int64), ("own_lo", C.c_int64), ("own_hi", C.c_int64),
+                ("need_lo", C.c_int64), ("need_hi", C.c_int64), ("frame_offset", C.c_int64)]
+
+
 def build(force: bool = False) -> Path:
     """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU)."""
     if force or not LIB_PATH.exists():
@@ -90,6 +95,17 @@ def lib() -> C.CDLL:
     L.mlx_pv_run.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mlx_pv_run_dev.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mlx_pv_phase_totals_dev.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mlx_pv_analyze_dev.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mlx_pv_synth_dev.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp)]
+    L.mlx_shard_frames.argtypes = [i64, i32, i32, i32, i32, C.POINTER(TimeShardC)]
+    L.mlx_comm_unique_id.argtypes = [vp]
+    L.mlx_comm_create.argtypes = [C.POINTER(vp), vp, vp, i32, i32]
+    L.mlx_comm_destroy.argtypes = [vp]
+    L.mlx_comm_destroy.restype = None
+    L.mlx_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.mlx_pv_run_sharded_dev.argtypes = [vp, vp, C.POINTER(PvParams), C.POINTER(vp), i32, i64,
+                                         C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mlx_pv_run_sharded.argtypes = L.mlx_pv_run_sharded_dev.argtypes
     L.mlx_pv_process_host.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(i64), i32,
                                       C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mlx_grain_render.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp]

@@ -14,109 +14,19 @@
 #include <string>
 #include <vector>
 
-#include "../../include/melonix_gpu.h"
-#include "kernels.h"
+#include "capi_internal.h"
 
 using namespace mlx;
 
-namespace {
-
+namespace mlx {
 thread_local std::string g_err;
-
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+}  // namespace mlx
 
-#define CK(expr)                                                                          \
-  do {                                                                                    \
-    cudaError_t e_ = (expr);                                                              \
-    if (e_ != cudaSuccess)                                                                \
-      return fail(e_ == cudaErrorMemoryAllocation ? MLX_ERR_NOMEM : MLX_ERR_CUDA,         \
-                  std::string(#expr) + ": " + cudaGetErrorString(e_));                    \
-  } while (0)
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t reserve(size_t want) {
-    if (want <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) bytes = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-  }
-};
-
-struct Tables {
-  DevBuf tw_d, twr_d, tw_f, twr_f, win, win_d, wsyn, decay;
-  bool pv_ready = false, spec_ready = false;
-};
-
-struct Track {
-  size_t offset = 0;  // floats from the base of the track buffer to sample 0
-  int64_t n = 0;
-};
-
-}  // namespace
-
-struct mlx_ctx {
-  int device = 0;
-  int sm_count = 0, cc = 0;
-  size_t total_mem = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of mlx_pv_process_host
-  int64_t launches = 0;
-
-  // optional per-kernel timing: one event before every launch, one after the last of a sequence
-  bool profiling = false;
-  std::vector<cudaEvent_t> ev_pool;
-  std::vector<int> ev_kind;  // kind of the launch that follows mark i; -1 = end of sequence
-  void mark(int kind) {
-    if (!profiling) return;
-    if (ev_kind.size() == ev_pool.size()) {
-      cudaEvent_t e;
-      if (cudaEventCreate(&e) != cudaSuccess) return;
-      ev_pool.push_back(e);
-    }
-    cudaEventRecord(ev_pool[ev_kind.size()], stream);
-    ev_kind.push_back(kind);
-  }
-
-  DevBuf track_buf;
-  std::vector<Track> tracks;
-
-  std::map<int, Tables> tables;
-
-  // phase-vocoder scratch
-  DevBuf smag, lacc, tot, totc, pre, carry, track_desc, ptr_stage, gk;
-  DevBuf out_wav, out_peak, out_f0;  // device results for the host-pointer entry points
-  DevBuf jobs, spec_out, spec_rgb;
-  DevBuf g_i32a, g_i32b, g_f32a, g_f32b, g_i64, g_out, g_out16;
-  DevBuf seg_bits, seg_desc, seg_rows, seg_count;  // grain segmentation scratch
-  DevBuf picks, picks_ranges, picks_out, picks_desc;  // min/max pyramid of track `picks_track` + query staging
-  int picks_track = -1;
-  // pinned staging ring for per-call descriptors / tables: a slot is reused only after the copies
-  // that read it have completed (event), so launches never wait on the host.
-  struct Slot {
-    void* p = nullptr;
-    size_t bytes = 0;
-    cudaEvent_t done = nullptr;
-  };
-  Slot slots[8];
-  int next_slot = 0;
-
-  const float* track_ptr(int t) const { return static_cast<const float*>(track_buf.p) + tracks[t].offset; }
-};
-
-namespace {
+namespace mlx {
 
 // next staging slot of at least `bytes` (waits only if the GPU is 8 calls behind)
 int acquire_slot(mlx_ctx* c, size_t bytes, mlx_ctx::Slot** out) {
@@ -207,6 +117,7 @@ int layout_tracks(mlx_ctx* c, const int64_t* n, int ntracks) {
   if (ntracks <= 0 || !n) return fail(MLX_ERR_INVALID, "ntracks must be > 0");
   c->tracks.assign(ntracks, Track{});
   c->picks_track = -1;  // a cached pyramid belongs to the previous upload
+  c->staged.valid = false;
   size_t off = 0;
   for (int t = 0; t < ntracks; ++t) {
     if (n[t] < 0 || n[t] > (int64_t)0x7fffffff - 65536)
@@ -224,12 +135,6 @@ int layout_tracks(mlx_ctx* c, const int64_t* n, int ntracks) {
 
 int64_t num_frames(int64_t n, int hop) { return (n + hop - 1) / hop; }
 
-struct PvPlan {
-  int N, H, G, NBP;
-  int CA, CS;
-  int64_t fb, fe, Fmax;
-  int64_t wave_frames;
-};
 
 int pv_validate(mlx_ctx* c, const mlx_pv_params* p, PvPlan* pl) {
   if (!c || !p) return fail(MLX_ERR_INVALID, "null argument");
@@ -286,11 +191,6 @@ int pv_validate(mlx_ctx* c, const mlx_pv_params* p, PvPlan* pl) {
 // Stages everything a run needs on the device BEFORE any bulk copy is queued: track descriptors,
 // the bin-shift table of the constant rate, zeroed / carried-in phase.  (Small H2D copies issued
 // later would queue behind gigabytes of uploads on the single H2D copy engine.)
-struct PvPrepared {
-  const PvTrack* tdev = nullptr;  // [ntracks]
-  uint32_t* carry = nullptr;      // [ntracks][NBP]
-  Tables* tb = nullptr;
-};
 
 int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* const* out_wav,
                int32_t* const* out_peak, float* const* out_f0, PvPrepared* out) {
@@ -349,16 +249,31 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
 // Launches waves of K_A -> scan (-> K_S) over frames [fb, fe) of `nt` prepared tracks starting at
 // `first`.  Issues kernels only (plus optional D2D copies of the phase totals): nothing here touches
 // the H2D copy engine.
+//   kPvAll      K_A, scan, K_S per wave (synth = false: no K_S)
+//   kPvAnalyze  K_A + scan(carry = 0) over ONE wave; smag / lacc / tot / totc stay staged in HBM and the
+//               carry holds the phase totals of the owned frames
+//   kPvSynth    scan(carry = phase_in) + K_S on the staged wave: the scan is re-run because the prefix of
+//               every chunk moves with the carried-in phase (it reads tot / totc only: microseconds)
 int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrepared& pr, int first, int nt,
-              bool synth, uint32_t* const* totals_dev) {
+              bool synth, uint32_t* const* totals_dev, PvMode mode) {
   Tables* tb = pr.tb;
   const size_t rows = (size_t)pl.wave_frames + 3;
   const size_t nchunksA_max = (size_t)((pl.wave_frames + 3 + pl.CA - 1) / pl.CA);
-  CK(c->smag.reserve(sizeof(float) * nt * rows * pl.NBP));
-  CK(c->lacc.reserve(sizeof(uint32_t) * nt * rows * pl.NBP));
-  CK(c->tot.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
-  CK(c->totc.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
-  CK(c->pre.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
+  if (mode != kPvAll && pl.wave_frames < pl.fe - pl.fb)
+    return fail(MLX_ERR_UNSUPPORTED, "the split analyze / synth calls need the frame range in one wave (wave_mib < 0)");
+  if (mode == kPvSynth) {
+    const mlx_ctx::Staged& sg = c->staged;
+    if (!sg.valid || sg.N != pl.N || sg.rate != p->rate || sg.fb != pl.fb || sg.fe != pl.fe || sg.first != first ||
+        sg.nt != nt || sg.CA != pl.CA || sg.wave_frames != pl.wave_frames)
+      return fail(MLX_ERR_STATE, "mlx_pv_synth_dev: no staged analysis with these parameters (call mlx_pv_analyze_dev first)");
+  } else {
+    c->staged.valid = false;  // the scratch is about to be overwritten
+    CK(c->smag.reserve(sizeof(float) * nt * rows * pl.NBP));
+    CK(c->lacc.reserve(sizeof(uint32_t) * nt * rows * pl.NBP));
+    CK(c->tot.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
+    CK(c->totc.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
+    CK(c->pre.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
+  }
 
   PvTables pt{static_cast<const cplx<double>*>(tb->tw_d.p), static_cast<const cplx<double>*>(tb->twr_d.p),
               static_cast<const cplx<float>*>(tb->tw_f.p),  static_cast<const cplx<float>*>(tb->twr_f.p),
@@ -389,18 +304,33 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
     wv.kmax = kmax;
     wv.gk = static_cast<const uint32_t*>(c->gk.p);
     wv.r_fix = (long long)((double)p->rate * 67108864.0);
-    c->mark(0);
-    CK(launch_pv_analyze(pl.N, tdev, nt, wv, pt, sc, c->stream));
+    if (mode != kPvSynth) {
+      c->mark(0);
+      CK(launch_pv_analyze(pl.N, tdev, nt, wv, pt, sc, c->stream));
+      c->launches += 1;
+    }
     c->mark(1);
     CK(launch_pv_scan(pl.N, nt, wv, sc, c->stream));
-    c->launches += 2;
-    if (synth) {
+    c->launches += 1;
+    if (synth && mode != kPvAnalyze) {
       c->mark(2);
       CK(launch_pv_synth(pl.N, tdev, nt, wv, pt, sc, c->stream));
       c->launches += 1;
     }
   }
   c->mark(-1);
+  if (mode == kPvAnalyze) {
+    mlx_ctx::Staged& sg = c->staged;
+    sg.valid = true;
+    sg.N = pl.N;
+    sg.rate = p->rate;
+    sg.fb = pl.fb;
+    sg.fe = pl.fe;
+    sg.first = first;
+    sg.nt = nt;
+    sg.CA = pl.CA;
+    sg.wave_frames = pl.wave_frames;
+  }
   if (totals_dev) {
     for (int t = 0; t < nt; ++t)
       if (totals_dev[t])
@@ -412,18 +342,18 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
 
 // prepare + launch over all uploaded tracks
 int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth, float* const* out_wav,
-               int32_t* const* out_peak, float* const* out_f0, uint32_t* const* totals_dev) {
+               int32_t* const* out_peak, float* const* out_f0, uint32_t* const* totals_dev, PvMode mode) {
   PvPrepared pr;
   int rc = pv_prepare(c, p, pl.N, synth, out_wav, out_peak, out_f0, &pr);
   if (rc) return rc;
-  return pv_launch(c, p, pl, pr, 0, (int)c->tracks.size(), synth, totals_dev);
+  return pv_launch(c, p, pl, pr, 0, (int)c->tracks.size(), synth, totals_dev, mode);
 }
 
-}  // namespace
+}  // namespace mlx
 
 extern "C" {
 
-const char* mlx_last_error(void) { return g_err.c_str(); }
+const char* mlx_last_error(void) { return mlx::g_err.c_str(); }
 
 int mlx_create(mlx_ctx** out, int device) {
   if (!out) return fail(MLX_ERR_INVALID, "out is null");
@@ -664,7 +594,7 @@ int mlx_pv_run_dev(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav_dev
   int rc = pv_validate(c, p, &pl);
   if (rc) return rc;
   CK(cudaSetDevice(c->device));
-  return pv_execute(c, p, pl, true, out_wav_dev, out_peak_dev, out_f0_dev, nullptr);
+  return pv_execute(c, p, pl, true, out_wav_dev, out_peak_dev, out_f0_dev, nullptr, kPvAll);
 }
 
 int mlx_pv_phase_totals_dev(mlx_ctx* c, const mlx_pv_params* p, uint32_t* const* totals_dev,
@@ -676,7 +606,36 @@ int mlx_pv_phase_totals_dev(mlx_ctx* c, const mlx_pv_params* p, uint32_t* const*
   CK(cudaSetDevice(c->device));
   mlx_pv_params q = *p;
   q.phase_in_dev = nullptr;  // totals are relative to the first owned frame
-  return pv_execute(c, &q, pl, false, nullptr, out_peak_dev, out_f0_dev, totals_dev);
+  return pv_execute(c, &q, pl, false, nullptr, out_peak_dev, out_f0_dev, totals_dev, kPvAll);
+}
+
+int mlx_pv_analyze_dev(mlx_ctx* c, const mlx_pv_params* p, uint32_t* const* totals_dev,
+                       int32_t* const* out_peak_dev, float* const* out_f0_dev) {
+  PvPlan pl{};
+  mlx_pv_params q{};
+  if (p) {
+    q = *p;
+    q.wave_mib = -1;  // the staged intermediates must cover the whole range
+    q.phase_in_dev = nullptr;
+  }
+  int rc = pv_validate(c, p ? &q : nullptr, &pl);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  return pv_execute(c, &q, pl, false, nullptr, out_peak_dev, out_f0_dev, totals_dev, kPvAnalyze);
+}
+
+int mlx_pv_synth_dev(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav_dev) {
+  PvPlan pl{};
+  mlx_pv_params q{};
+  if (p) {
+    q = *p;
+    q.wave_mib = -1;
+  }
+  int rc = pv_validate(c, p ? &q : nullptr, &pl);
+  if (rc) return rc;
+  if (!out_wav_dev) return fail(MLX_ERR_INVALID, "out_wav_dev is null");
+  CK(cudaSetDevice(c->device));
+  return pv_execute(c, &q, pl, true, out_wav_dev, nullptr, nullptr, nullptr, kPvSynth);
 }
 
 int mlx_pv_run(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav, int32_t* const* out_peak,
@@ -703,7 +662,7 @@ int mlx_pv_run(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav, int32_
     if (out_f0 && out_f0[t]) df[t] = static_cast<float*>(c->out_f0.p) + foff[t];
   }
   rc = pv_execute(c, p, pl, true, out_wav ? dw.data() : nullptr, out_peak ? dp.data() : nullptr,
-                  out_f0 ? df.data() : nullptr, nullptr);
+                  out_f0 ? df.data() : nullptr, nullptr, kPvAll);
   if (rc) return rc;
   // copy back only what this call owns: hops / frames [fb, fe)
   for (int t = 0; t < nt; ++t) {
@@ -799,7 +758,7 @@ int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* 
     PvPlan pl{};
     result = pv_validate(c, p, &pl);
     if (result) break;
-    result = pv_launch(c, p, pl, pr, t, 1, true, nullptr);
+    result = pv_launch(c, p, pl, pr, t, 1, true, nullptr, kPvAll);
     if (result) break;
     cudaEventRecord(ev_done[t], c->stream);
     if (trace && t == 0) cudaEventRecord(tr_k_first, c->stream);

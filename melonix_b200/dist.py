@@ -5,7 +5,9 @@ Two sharding modes:
 * independent tracks (BASELINE configs[2]): `shard_tracks` -- contiguous blocks of tracks per rank,
   no data-path collective at all.
 * one long file sharded by contiguous time range (configs[3]): rank r owns frames
-  [F*r/G, F*(r+1)/G).  Two small exchanges per track:
+  [F*r/G, F*(r+1)/G).  The product path is `run_time_sharded`, a thin caller of the C ABI's
+  mlx_pv_run_sharded_dev (NCCL inside the library, csrc/multi.cu); `run_time_sharded_torch` runs the same
+  protocol with torch.distributed collectives.  Two small exchanges per track:
     1. seam samples: the analysis of a rank's first frame needs the `fftN` samples before its range
        (and one hop more for the halo frame), its last three overlap-add hops need `3*hop` samples
        after it -> one batched NCCL send/recv with each neighbour (`exchange_seam_samples`);
@@ -62,18 +64,18 @@ class TimeShard:
 
 
 def shard_frames(n: int, fft_n: int, hop: int, world: int, rank: int) -> TimeShard:
-    """Contiguous time-range shard of a track of n samples for `rank` of `world`."""
-    F = num_frames(n, hop)
-    fb = F * rank // world
-    fe = F * (rank + 1) // world
-    # frame f covers samples [(f-3)*hop, (f+1)*hop) (fft_n = 4*hop).  Needed frames: fb-1 (halo whose
-    # spectrum seeds the phase difference) .. fe+2 (their tails overlap-add into the owned hops).
-    off = max(fb - 4, 0)
-    need_lo = off * hop
-    need_hi = min(n, (fe + 3) * hop)
-    own_lo = min(n, fb * hop)
-    own_hi = min(n, fe * hop)
-    return TimeShard(rank, fb, fe, own_lo, own_hi, need_lo, need_hi, off)
+    """Contiguous time-range shard of a track of n samples for `rank` of `world`.  The rule lives in the
+    C ABI (mlx_shard_frames, csrc/multi.cu -- a pure host function, no GPU needed) so that the C++ and the
+    Python drivers cannot disagree: frame f covers samples [(f-3)*hop, (f+1)*hop) (fft_n = 4*hop); needed
+    frames are fb-1 (halo whose spectrum seeds the phase difference) .. fe+2 (their tails overlap-add
+    into the owned hops)."""
+    import ctypes as C
+
+    from . import capi
+    sh = capi.TimeShardC()
+    capi.check(capi.lib().mlx_shard_frames(int(n), int(fft_n), int(hop), int(world), int(rank), C.byref(sh)))
+    return TimeShard(rank, sh.frame_begin, sh.frame_end, sh.own_lo, sh.own_hi, sh.need_lo, sh.need_hi,
+                     sh.frame_offset)
 
 
 def exchange_seam_samples(own: torch.Tensor, shard: TimeShard, world: int, group=None) -> torch.Tensor:
@@ -137,15 +139,55 @@ def exclusive_phase_prefix(totals: torch.Tensor, world: int, rank: int, group=No
     return acc
 
 
+def make_comm(engine, group=None):
+    """One NCCL communicator behind the C ABI per rank (mlx_comm): rank 0 draws the unique id, the bytes
+    travel over the existing torch.distributed group (any backend), every rank joins."""
+    from .engine import Comm
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return Comm(engine, box[0], world, rank)
+
+
 def run_time_sharded(engine, owns, n_total: int, fft_n: int, hop: int, rate: float,
-                     sample_rate: float = 48000.0, group=None):
-    """Phase-vocodes long mono track(s) of n_total samples sharded by time range across the ranks of
-    `group` (BASELINE configs[3]: "stereo" = two planar mono tracks).
+                     sample_rate: float = 48000.0, group=None, comm=None, outs=None):
+    """Phase-vocodes long mono track(s) of n_total samples sharded by time range across the ranks
+    (BASELINE configs[3]: "stereo" = two planar mono tracks).  Thin caller of mlx_pv_run_sharded_dev:
+    seam send/recv, the single analysis pass, the phase-total all-gather and the synthesis all happen
+    behind the C ABI (csrc/multi.cu).
 
     owns: this rank's owned samples, one CUDA float32 tensor per track (global samples
     [own_lo, own_hi) of plan_time_shards(...)[rank]); a single tensor is accepted too.
-    Returns per track (y_own, peak_own, f0_own): the owned output samples and the owned frames' peak
-    bins / f0, on the device.  Bit-identical to the unsharded run."""
+    comm: a Comm from make_comm (created and cached on the engine when omitted).
+    outs: optional preallocated (ys, peaks, f0s) lists to write into.
+    Returns per track (y_own, peak_own, f0_own) on the device.  Bit-identical to the unsharded run."""
+    single = isinstance(owns, torch.Tensor)
+    owns = [owns] if single else list(owns)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if comm is None:
+        comm = getattr(engine, "_comm", None)
+        if comm is None or comm.world != world or comm.rank != rank:
+            comm = engine._comm = make_comm(engine, group)
+    shard = shard_frames(n_total, fft_n, hop, world, rank)
+    dev = owns[0].device
+    nf = shard.frame_end - shard.frame_begin
+    if outs is None:
+        ys = [torch.empty_like(o) for o in owns]
+        peaks = [torch.empty(nf, dtype=torch.int32, device=dev) for _ in owns]
+        f0s = [torch.empty(nf, dtype=torch.float32, device=dev) for _ in owns]
+    else:
+        ys, peaks, f0s = outs
+    engine.use_torch_stream()
+    engine.pv_run_sharded_dev(comm, owns, n_total, fft_n, hop, rate, ys, peaks, f0s, sample_rate=sample_rate)
+    out = list(zip(ys, peaks, f0s))
+    return out[0] if single else out
+
+
+def run_time_sharded_torch(engine, owns, n_total: int, fft_n: int, hop: int, rate: float,
+                           sample_rate: float = 48000.0, group=None):
+    """The same protocol with torch.distributed collectives around the split C-ABI calls
+    (mlx_pv_analyze_dev -> all_gather -> mlx_pv_synth_dev): for process groups whose transport is not
+    the library's own NCCL communicator.  One analysis pass as well; bit-identical results."""
     single = isinstance(owns, torch.Tensor)
     owns = [owns] if single else list(owns)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -161,15 +203,14 @@ def run_time_sharded(engine, owns, n_total: int, fft_n: int, hop: int, rate: flo
     totals32 = torch.zeros((nt, nb), dtype=torch.int32, device=dev)
     peak = torch.zeros((nt, F_local), dtype=torch.int32, device=dev)
     f0 = torch.zeros((nt, F_local), dtype=torch.float32, device=dev)
-    engine.pv_phase_totals_dev(fft_n, hop, rate, [totals32[t] for t in range(nt)], sample_rate=sample_rate,
-                               frame_begin=lb, frame_end=le, wave_mib=-1)
+    engine.pv_analyze_dev(fft_n, hop, rate, [totals32[t] for t in range(nt)], [peak[t] for t in range(nt)],
+                          [f0[t] for t in range(nt)], sample_rate=sample_rate, frame_begin=lb, frame_end=le)
     totals = totals32.to(torch.int64) & 0xFFFFFFFF
     carry = exclusive_phase_prefix(totals, world, rank, group)                  # phase carry (2)
     carry32 = torch.where(carry >= 2 ** 31, carry - 2 ** 32, carry).to(torch.int32).contiguous()
     ys = [torch.zeros_like(w) for w in windows]
-    engine.pv_run_dev(fft_n, hop, rate, ys, [peak[t] for t in range(nt)], [f0[t] for t in range(nt)],
-                      sample_rate=sample_rate, frame_begin=lb, frame_end=le,
-                      phase_in=[carry32[t] for t in range(nt)], wave_mib=-1)
+    engine.pv_synth_dev(fft_n, hop, rate, ys, sample_rate=sample_rate, frame_begin=lb, frame_end=le,
+                        phase_in=[carry32[t] for t in range(nt)])
     lo = shard.left_halo
     out = [(ys[t][lo:lo + owns[t].numel()], peak[t, lb:le], f0[t, lb:le]) for t in range(nt)]
     return out[0] if single else out

@@ -172,6 +172,40 @@ class Engine:
         pf = ptr_array([t.data_ptr() if t is not None else None for t in (out_f0 or [None] * nt)])
         check(self._L.mlx_pv_phase_totals_dev(self._h, C.byref(p), pt, pp, pf))
 
+    def pv_analyze_dev(self, fftN: int, hop: int, rate: float, totals, out_peak=None, out_f0=None,
+                       sample_rate: float = 48000.0, frame_begin: int = -1, frame_end: int = -1) -> None:
+        """First half of the split pipeline (mlx_pv_analyze_dev): ONE analysis pass; the intermediates stay
+        staged on the device, `totals` (list of int32/uint32 CUDA tensors of fftN/2+1) receive the phase
+        totals of the owned frames."""
+        p = self._params(fftN, hop, rate, sample_rate, frame_begin, frame_end, -1)
+        nt = len(self._lens)
+        pt = ptr_array([t.data_ptr() if t is not None else None for t in totals])
+        pp = ptr_array([t.data_ptr() if t is not None else None for t in (out_peak or [None] * nt)])
+        pf = ptr_array([t.data_ptr() if t is not None else None for t in (out_f0 or [None] * nt)])
+        check(self._L.mlx_pv_analyze_dev(self._h, C.byref(p), pt, pp, pf))
+
+    def pv_synth_dev(self, fftN: int, hop: int, rate: float, out_wav, sample_rate: float = 48000.0,
+                     frame_begin: int = -1, frame_end: int = -1, phase_in=None) -> None:
+        """Second half (mlx_pv_synth_dev): carried-in phase + synthesis on the staged analysis."""
+        p = self._params(fftN, hop, rate, sample_rate, frame_begin, frame_end, -1, phase_in)
+        pw = ptr_array([t.data_ptr() if t is not None else None for t in out_wav])
+        check(self._L.mlx_pv_synth_dev(self._h, C.byref(p), pw))
+
+    def pv_run_sharded_dev(self, comm: "Comm", owns, n_total: int, fftN: int, hop: int, rate: float, out_own,
+                           peak_own=None, f0_own=None, sample_rate: float = 48000.0) -> None:
+        """One long file by time range across the ranks of `comm` (mlx_pv_run_sharded_dev): owns / out_own
+        are lists (one per planar channel) of CUDA tensors holding this rank's owned samples."""
+        p = self._params(fftN, hop, rate, sample_rate)
+        nt = len(owns)
+        po = ptr_array([t.data_ptr() for t in owns])
+        pw = ptr_array([t.data_ptr() if t is not None else None for t in (out_own or [None] * nt)])
+        pp = ptr_array([t.data_ptr() if t is not None else None for t in (peak_own or [None] * nt)])
+        pf = ptr_array([t.data_ptr() if t is not None else None for t in (f0_own or [None] * nt)])
+        check(self._L.mlx_pv_run_sharded_dev(self._h, comm._h, C.byref(p), po, nt, int(n_total),
+                                             pw if out_own else None, pp if peak_own else None,
+                                             pf if f0_own else None))
+        self._lens = [int(self._L.mlx_track_len(self._h, t)) for t in range(nt)]
+
     def pv_process_host(self, tracks, fftN: int, hop: int, rate: float, out_wav, out_peak=None,
                         out_f0=None, sample_rate: float = 48000.0, wave_mib: int = 0) -> None:
         """End to end from host buffers (numpy arrays or pinned torch CPU tensors) into host buffers."""
@@ -263,3 +297,34 @@ class Engine:
                                        oo.ctypes.data, gn.ctypes.data, ng, tail_zeros, out.ctypes.data,
                                        out16.ctypes.data if want_i16 else None))
         return out, out16
+
+
+class Comm:
+    """NCCL communicator behind the C ABI (mlx_comm): one per rank, bound to the rank's Engine."""
+
+    def __init__(self, engine: Engine, unique_id: bytes, world: int, rank: int):
+        assert len(unique_id) == 128
+        self._L = engine._L
+        self.engine = engine
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self._L.mlx_comm_create(C.byref(h), engine._h, buf, int(world), int(rank)))
+        self._h = h
+        self.world, self.rank = int(world), int(rank)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(capi.lib().mlx_comm_unique_id(buf))
+        return buf.raw
+
+    @property
+    def nccl_version(self) -> int:
+        v = C.c_int()
+        check(self._L.mlx_comm_info(self._h, None, None, C.byref(v)))
+        return v.value
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.mlx_comm_destroy(self._h)
+            self._h = None

@@ -4,6 +4,7 @@
 //   host_test spec      wav.f32 jobs.i32 out.f32        Spec::getSpec for every job (async contract checked)
 //   host_test recolour  wav.f32 jobs.i32 k out.u8       getSpec, then getSpecRgb(k): served at once from the cached floats
 //   host_test speccache wav.f32 k width rangeTime out.u8   SpecCache::getTex for every column
+//   host_test shard     wav.f32 fftN rate ngpu out.f32   one file by time range over ngpu GPUs (one host thread each)
 //   host_test export    wav.f32 sampleRate semitones out.i16   segment -> schedule -> mlx_grain_render
 #include "grain_schedule.hpp"
 #include "spec-cache.hpp"
@@ -12,6 +13,7 @@
 #include "../../include/melonix_gpu.h"
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -183,6 +185,68 @@ static int runExport(char **a)
   return rc == MLX_OK ? 0 : 6;
 }
 
+// One long file phase-vocoded by time range across `ngpu` GPUs from a plain C++ host: one thread per
+// GPU, each with its own context and its rank of one NCCL communicator behind the C ABI
+// (mlx_comm_create); every rank hands in only its owned samples and receives only its owned output.
+static int runShard(char **a)
+{
+  const auto wav = readAll<float>(a[0]);
+  const int fftN = std::atoi(a[1]);
+  const float rate = std::strtof(a[2], nullptr); // the pitch ratio itself (%.9g round-trips a float exactly)
+  const int ngpu = std::atoi(a[3]);
+  const int64_t n = static_cast<int64_t>(wav.size());
+  std::vector<float> out(wav.size(), 0.f);
+  char id[128];
+  if (mlx_comm_unique_id(id) != MLX_OK)
+  {
+    std::fprintf(stderr, "%s\n", mlx_last_error());
+    return 5;
+  }
+  mlx_pv_params p{};
+  p.fftN = fftN;
+  p.hop = fftN / 4;
+  p.rate = rate;
+  p.sample_rate = 48000.0;
+  p.frame_begin = p.frame_end = -1;
+  std::vector<int> rcs(ngpu, 0);
+  std::vector<std::string> errs(ngpu);
+  std::vector<std::thread> ranks;
+  for (int r = 0; r < ngpu; ++r)
+    ranks.emplace_back([&, r] {
+      mlx_ctx *ctx = nullptr;
+      mlx_comm *comm = nullptr;
+      int rc = mlx_create(&ctx, r);
+      if (rc == MLX_OK)
+        rc = mlx_comm_create(&comm, ctx, id, ngpu, r);
+      mlx_time_shard sh{};
+      if (rc == MLX_OK)
+        rc = mlx_shard_frames(n, fftN, fftN / 4, ngpu, r, &sh);
+      if (rc == MLX_OK)
+      {
+        const float *own = wav.data() + sh.own_lo;
+        float *y = out.data() + sh.own_lo;
+        rc = mlx_pv_run_sharded(ctx, comm, &p, &own, 1, n, &y, nullptr, nullptr);
+      }
+      if (rc != MLX_OK)
+        errs[r] = mlx_last_error();
+      rcs[r] = rc;
+      mlx_comm_destroy(comm);
+      mlx_destroy(ctx);
+    });
+  for (auto &t : ranks)
+    t.join();
+  int bad = 0;
+  for (int r = 0; r < ngpu; ++r)
+    if (rcs[r] != MLX_OK)
+    {
+      std::fprintf(stderr, "rank %d: %s\n", r, errs[r].c_str());
+      ++bad;
+    }
+  writeAll(a[4], out.data(), out.size());
+  std::printf("shard: gpus=%d samples=%zu failed_ranks=%d\n", ngpu, out.size(), bad);
+  return bad ? 6 : 0;
+}
+
 int main(int argc, char **argv)
 {
   if (argc >= 5 && !std::strcmp(argv[1], "spec"))
@@ -191,8 +255,10 @@ int main(int argc, char **argv)
     return runRecolour(argv + 2);
   if (argc >= 7 && !std::strcmp(argv[1], "speccache"))
     return runSpecCache(argv + 2);
+  if (argc >= 7 && !std::strcmp(argv[1], "shard"))
+    return runShard(argv + 2);
   if (argc >= 6 && !std::strcmp(argv[1], "export"))
     return runExport(argv + 2);
-  std::fprintf(stderr, "usage: host_test spec|recolour|speccache|export ...\n");
+  std::fprintf(stderr, "usage: host_test spec|recolour|speccache|shard|export ...\n");
   return 1;
 }

@@ -38,6 +38,23 @@ def test_time_shards_cover_and_halo():
             assert sh[1].left_halo == N and sh[0].right_halo == 3 * H  # the seam payloads
 
 
+def test_c_abi_shard_rule_matches_closed_form():
+    """mlx_shard_frames (pure host function of libmelonix_b200.so; loads without a GPU) against the rule
+    restated here: ragged lengths, more ranks than frames, single rank."""
+    for n in (0, 1, 511, 512, 513, 48000 * 3 + 77, 345_600_000):
+        for N in (512, 2048, 4096):
+            H = N // 4
+            F = (n + H - 1) // H
+            for w in (1, 2, 3, 8):
+                for r in range(w):
+                    s = D.shard_frames(n, N, H, w, r)
+                    fb, fe = F * r // w, F * (r + 1) // w
+                    off = max(fb - 4, 0)
+                    assert (s.frame_begin, s.frame_end, s.frame_offset) == (fb, fe, off)
+                    assert (s.own_lo, s.own_hi) == (min(n, fb * H), min(n, fe * H))
+                    assert (s.need_lo, s.need_hi) == (off * H, min(n, (fe + 3) * H))
+
+
 def _worker(rank, world, port, n, N, H, out):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:

@@ -210,7 +210,9 @@ def test_grain_segmentation_golden(engine):
 
 def test_grain_segmentation_two_hour_track(engine):
     """BASELINE configs[3] length (2 h at 48 kHz, 345.6 M samples): positions beyond 2^28, ~10.8 M words of
-    crossing bits, ~1300 stage refills in the chain; against the host C++ mirror (the oracle's twin)."""
+    crossing bits, ~1300 stage refills in the chain; against the ORACLE (oracle/grain_ref.c, pinned to the
+    reference's own App::preproc in tests/test_oracle.py) and the product's host mirror."""
+    from oracle import oracle as O
     from melonix_b200 import hostlib as H
     base = S.vibrato_tone(60.0, seed=21)
     x = np.tile(base, 120)
@@ -218,8 +220,10 @@ def test_grain_segmentation_two_hour_track(engine):
     assert x.size == 345_600_000
     engine.upload_tracks([x])
     gs, gl = engine.grain_segment()[0]
+    os_, ol = O.grain_segment(x)
+    assert gs.size == os_.size > 200_000
+    assert np.array_equal(gs, os_) and np.array_equal(gl, ol)
     hs, hl = H.grain_segment(x)
-    assert gs.size == hs.size > 200_000
     assert np.array_equal(gs, hs) and np.array_equal(gl, hl)
     assert int(gs[-1]) > (1 << 28)
     engine.upload_tracks([np.zeros(16, np.float32)])   # release the 1.4 GB track buffer for later tests

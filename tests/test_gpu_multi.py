@@ -25,3 +25,37 @@ def test_time_sharded_nccl_equals_unsharded(world):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "bitwise_equal=True" in r.stdout
+
+
+def _host_test(*args):
+    exe = ROOT / "melonix_b200" / "host_test"
+    assert exe.exists(), "run __graft_entry__.build()"
+    return subprocess.run([str(exe), *map(str, args)], capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.parametrize("ngpu", [1, 2, 4])
+def test_cpp_host_shards_one_file_without_python(tmp_path, ngpu):
+    """A plain C++ host (melonix_b200/host/host_test.cpp `shard`): one thread per GPU, each with its own
+    mlx_ctx and its rank of the NCCL communicator behind the C ABI (mlx_comm_create), hands in its owned
+    samples through mlx_pv_run_sharded and gets its owned output -- equal, bit for bit, to the unsharded
+    run.  ngpu = 1 exercises the same entry points on a single-GPU box."""
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "tests"))
+    import signals as S
+    import melonix_b200 as m
+    if _ngpu() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    x = S.vibrato_tone(30.0, seed=77)
+    x.tofile(tmp_path / "wav.f32")
+    r = _host_test("shard", tmp_path / "wav.f32", 4096, "%.9g" % float(m.semitone_ratio(3.0)), ngpu,
+                   tmp_path / "out.f32")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "failed_ranks=0" in r.stdout
+    got = np.fromfile(tmp_path / "out.f32", np.float32)
+    eng = m.Engine(0)
+    try:
+        eng.upload_tracks([x])
+        full = eng.pv_run(4096, 1024, m.semitone_ratio(3.0))[0]
+    finally:
+        eng.close()
+    assert np.array_equal(got, full["y"])

@@ -180,6 +180,115 @@ def test_time_range_shards_equal_unsharded_bitwise(engine):
         assert np.array_equal(peak, full["peak"])
 
 
+def test_split_analyze_synth_is_bitwise_the_one_call_pipeline(engine):
+    """mlx_pv_analyze_dev + mlx_pv_synth_dev (ONE analysis pass, intermediates staged on the device) equal
+    mlx_pv_run_dev bit for bit -- whole tracks, a ragged batch, and logical time shards with a carried-in
+    phase (the configs[3] protocol without the second analysis pass round 1 needed)."""
+    import torch
+    from melonix_b200 import dist as D
+    import melonix_b200 as m
+    engine.use_torch_stream()
+    # (a) whole tracks, ragged batch, pitch up and down
+    xs = [S.vibrato_tone(5.0, seed=61), S.vibrato_tone(3.3, seed=62)]
+    for N, semis in ((2048, 3.0), (2048, -5.0), (4096, 3.0), (1024, 7.0)):
+        H = N // 4
+        r = ratio(semis)
+        engine.upload_tracks(xs)
+        ref = engine.pv_run(N, H, r)
+        nb = N // 2 + 1
+        tots = [torch.zeros(nb, dtype=torch.int32, device="cuda") for _ in xs]
+        pks = [torch.zeros((x.size + H - 1) // H, dtype=torch.int32, device="cuda") for x in xs]
+        f0s = [torch.zeros((x.size + H - 1) // H, dtype=torch.float32, device="cuda") for x in xs]
+        ys = [torch.zeros(x.size, dtype=torch.float32, device="cuda") for x in xs]
+        engine.pv_analyze_dev(N, H, r, tots, pks, f0s)
+        engine.pv_synth_dev(N, H, r, ys)
+        torch.cuda.synchronize()
+        for u, y, pk, f0 in zip(ref, ys, pks, f0s):
+            assert np.array_equal(u["y"], y.cpu().numpy()), (N, semis)
+            assert np.array_equal(u["peak"], pk.cpu().numpy()) and np.array_equal(u["f0"], f0.cpu().numpy())
+        # the totals equal those of the analysis-only entry point
+        t2 = [torch.zeros(nb, dtype=torch.int32, device="cuda") for _ in xs]
+        engine.pv_phase_totals_dev(N, H, r, t2, wave_mib=-1)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(tots, t2))
+    # (b) synth without a staged analysis must fail loudly, not synthesise stale data
+    engine.upload_tracks(xs)
+    with pytest.raises(m.MlxError):
+        engine.pv_synth_dev(2048, 512, ratio(3.0), [torch.zeros(x.size, dtype=torch.float32, device="cuda") for x in xs])
+    # (c) logical shards on one GPU
+    N, H = 4096, 1024
+    x = S.vibrato_tone(20.0, seed=31)
+    r = ratio(3.0)
+    engine.upload_tracks([x])
+    full = engine.pv_run(N, H, r)[0]
+    xd = torch.from_numpy(x).cuda()
+    for world in (3,):
+        carry = torch.zeros(N // 2 + 1, dtype=torch.int64, device="cuda")
+        y = np.zeros_like(x)
+        for s in D.plan_time_shards(x.size, N, H, world):
+            win = xd[s.need_lo:s.need_hi].contiguous()
+            engine.upload_tracks_dev([win])
+            tot = torch.zeros(N // 2 + 1, dtype=torch.int32, device="cuda")
+            engine.pv_analyze_dev(N, H, r, [tot], frame_begin=s.local_frame_begin, frame_end=s.local_frame_end)
+            c32 = torch.where(carry >= 2 ** 31, carry - 2 ** 32, carry).to(torch.int32)
+            yd = torch.zeros_like(win)
+            engine.pv_synth_dev(N, H, r, [yd], frame_begin=s.local_frame_begin, frame_end=s.local_frame_end,
+                                phase_in=[c32])
+            torch.cuda.synchronize()
+            y[s.own_lo:s.own_hi] = yd[s.left_halo:s.left_halo + (s.own_hi - s.own_lo)].cpu().numpy()
+            carry = (carry + (tot.to(torch.int64) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        assert np.array_equal(y, full["y"]), f"world={world}"
+
+
+def test_bench_tracks_full_length_against_oracle(engine, oracle):
+    """Two real bench tracks (BASELINE configs[2] as bench.py generates them on the device: 300 s, per-track
+    f_base, seeds 1234 + track): tracks 0 and 63 against the oracle at full length."""
+    import torch
+    import bench as B
+    dev = torch.device("cuda", 0)
+    n = 300 * 48000
+    r = ratio(3.0)
+    for track in (0, 63):
+        # gen_tracks_gpu(rank = track, ntracks = 1) produces global track `track` of the bench batch
+        xt = B.gen_tracks_gpu(torch, dev, 1, n, track)[0].cpu().numpy()
+        engine.upload_tracks([xt])
+        g = engine.pv_run(2048, 512, r)[0]
+        o = oracle.pv_run(xt, 2048, 512, r)
+        excluded = check(g, o)
+        assert excluded == 0 and rms(g["y"], o["y"]) < 1e-6, track
+        # the far end of the track is as exact as its start (no drift over 28 125 frames)
+        assert rms(g["y"][-480000:], o["y"][-480000:]) < 1e-6
+
+
+def test_sinusoid_in_shifted_sinusoid_out(engine):
+    """A check that shares no code with either restatement of the spec: a steady sinusoid in gives a
+    sinusoid at rate * f out (frequency read off the output by a zero-padded FFT in numpy, double), with
+    steady amplitude, and the detected f0 / peak bin of the analysis matches the input tone."""
+    fs, N, H = 48000.0, 2048, 512
+    n = 4 * 48000
+    t = np.arange(n) / fs
+    for f_in, semis in ((440.0, 3.0), (997.0, -4.0), (233.3, 7.0)):
+        x = (0.4 * np.sin(2 * np.pi * f_in * t)).astype(np.float32)
+        r = float(ratio(semis))
+        engine.upload_tracks([x])
+        g = engine.pv_run(N, H, ratio(semis))[0]
+        # analysis side: detected pitch
+        mid = slice(8, g["f0"].size - 8)
+        assert np.all(g["peak"][mid] == int(round(f_in * N / fs)))
+        assert np.abs(g["f0"][mid] - f_in).max() < 1e-3
+        # synthesis side: output frequency and amplitude steadiness on the interior
+        y = g["y"][48000:-48000].astype(np.float64)
+        w = np.hanning(y.size)
+        Y = np.abs(np.fft.rfft(y * w, 1 << 20))
+        k = int(np.argmax(Y))
+        a, b, c = np.log(Y[k - 1]), np.log(Y[k]), np.log(Y[k + 1])
+        f_out = (k + 0.5 * (a - c) / (a - 2 * b + c)) * fs / (1 << 20)
+        assert abs(f_out - r * f_in) < 1e-3, (f_in, semis, f_out)   # the double oracle lands within 5e-6 Hz
+        env = np.sqrt(np.convolve(y * y, np.ones(4800) / 4800, "valid") * 2.0)
+        # (bin remapping spreads the main lobe: the level drops by a ratio-dependent factor but must be steady)
+        assert env.min() > 0.35 * 0.4 and env.max() < 1.0 * 0.4 and env.max() / env.min() < 1.02
+
+
 def test_per_frame_rate_array(engine, oracle):
     import torch
     x = S.vibrato_tone(2.0, seed=41)

@@ -1,15 +1,11 @@
-"""-m gpu, OPT-IN (MLX_RUN_DROPIN_GPU=1): the reference's own front-end on the product's GPU classes.
+"""-m gpu: the reference's own front-end on the product's GPU classes.
 
 oracle/_ref/libapp_dropin.so is what INTEGRATION.md section 1 produces: /root/reference/app.cpp and
 save-wav.cpp, unmodified, compiled against melonix_b200/host/{spec,spec-cache,range,texture} and linked
 with libmelonix_b200.so (oracle/Makefile target `dropin`; it travels to the GPU box prebuilt).  The test
 drives the reference's App through it -- preproc() constructs OUR Spec on the B200, SpecCache::getTex
 uploads OUR fused colour-ramp texels through the recording GL shim -- and compares every column with
-the all-reference build (oracle/_ref/libapp_ref.so, CPU).
-
-Written at the end of round 1 after the GPU budget was spent: its CPU half is covered by
-tests/test_host_side.py (the build links; without a GPU it stops in Spec's constructor), the GPU half
-has not run yet, hence the opt-in switch instead of a default-on test nobody has seen pass."""
+the all-reference build (oracle/_ref/libapp_ref.so, CPU)."""
 import os
 import sys
 from pathlib import Path
@@ -20,9 +16,7 @@ import pytest
 sys.path.insert(0, str(Path(__file__).resolve().parent))
 import signals as S  # noqa: E402
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MLX_RUN_DROPIN_GPU") != "1",
-                                 reason="opt-in: set MLX_RUN_DROPIN_GPU=1 (not yet validated on a B200)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_reference_front_end_on_gpu_spec_matches_all_reference_build(oracle):

@@ -34,8 +34,10 @@ def main():
     shard = D.plan_time_shards(x.size, N, H, world)[rank]
     own = torch.from_numpy(x[shard.own_lo:shard.own_hi]).cuda()
     eng = m.Engine(local)
-    y_own, peak_own, f0_own = D.run_time_sharded(eng, own, x.size, N, H, rate)
+    y_own, peak_own, f0_own = D.run_time_sharded(eng, own, x.size, N, H, rate)     # NCCL behind the C ABI
+    y_t, peak_t, f0_t = D.run_time_sharded_torch(eng, own, x.size, N, H, rate)    # torch.distributed collectives
     torch.cuda.synchronize()
+    same_paths = bool(torch.equal(y_own, y_t) and torch.equal(peak_own, peak_t) and torch.equal(f0_own, f0_t))
     # gather on rank 0
     sizes = [s.own_hi - s.own_lo for s in D.plan_time_shards(x.size, N, H, world)]
     pad = max(sizes)
@@ -48,11 +50,14 @@ def main():
         y = np.concatenate([g[:sz].cpu().numpy() for g, sz in zip(gathered, sizes)])
         eng.upload_tracks([x])
         full = eng.pv_run(N, H, rate)[0]
-        ok = bool(np.array_equal(y, full["y"]))
+        ok = bool(np.array_equal(y, full["y"])) and same_paths
         print(f"sharded_check world={world} N={N} seconds={seconds}: bitwise_equal={ok} "
               f"max|diff|={float(np.abs(y - full['y']).max()):.3e} seam_payload_floats=({N},{3 * H})", flush=True)
-    flag = torch.tensor([1 if ok else 0], device="cuda")
+    flag = torch.tensor([1 if (ok and same_paths) else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.broadcast(flag, 0)
+    if rank == 0 and int(flag.item()) != 1:
+        print("sharded_check: some rank disagrees (C-ABI NCCL path vs torch path, or vs unsharded)", flush=True)
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
