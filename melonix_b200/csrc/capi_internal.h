@@ -126,6 +126,7 @@ struct PvPrepared {
   const PvTrack* tdev = nullptr;  // [ntracks]
   uint32_t* carry = nullptr;      // [ntracks][NBP]
   Tables* tb = nullptr;
+  bool scatter_ok = false;        // the constant-rate pitch-up analysis kernel (K_A2) applies
 };
 
 enum PvMode { kPvAll = 0, kPvAnalyze = 1, kPvSynth = 2 };

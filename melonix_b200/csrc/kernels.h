@@ -48,6 +48,10 @@ struct PvWave {
   //   gk[j] = klo | khi << 16 with K_j = [klo, khi] (klo = 1, khi = 0 when empty)
   const uint32_t* gk;
   long long r_fix;  // rate * 2^26, exact (a float has 24 significant bits)
+  // scatter form of the same map for the constant-rate pitch-up kernel K_A2 (nullptr: not eligible):
+  //   dst[k] = j | nz << 16 with j = trunc(float(k) * rate) <= fftN/2 the output bin fed by input bin k and
+  //   nz the empty output bins that follow j;  0xffffffff when j lies beyond the Nyquist bin
+  const uint32_t* dst;
 };
 
 struct PvScratch {
@@ -73,6 +77,13 @@ cudaError_t launch_pv_scan(int fftN, int ntracks, const PvWave& wv, const PvScra
 cudaError_t launch_pv_synth(int fftN, const PvTrack* tracks_dev, int ntracks, const PvWave& wv,
                             const PvTables& tb, const PvScratch& sc, cudaStream_t st);
 cudaError_t pv_configure(int fftN);  // cudaFuncSetAttribute for the instantiation
+// K_A2 (pv_analyze2.cu): constant rate >= 1, fftN in {1024, 2048}; bit-identical to launch_pv_analyze
+bool pv_analyze2_supported(int fftN);
+int pv_analyze2_band_capacity(int fftN);  // largest kmax - kmin + 1 its peak search holds
+int pv_analyze2_frames_per_batch(int fftN);
+cudaError_t pv_analyze2_configure(int fftN);
+cudaError_t launch_pv_analyze2(int fftN, const PvTrack* tracks_dev, int ntracks, const PvWave& wv,
+                               const PvTables& tb, const PvScratch& sc, cudaStream_t st);
 
 // ---- Spec
 struct SpecArgs {

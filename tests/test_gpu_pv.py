@@ -289,6 +289,45 @@ def test_sinusoid_in_shifted_sinusoid_out(engine):
         assert env.min() > 0.35 * 0.4 and env.max() < 1.0 * 0.4 and env.max() / env.min() < 1.02
 
 
+@pytest.mark.parametrize("N", [1024, 2048])
+def test_pitch_up_kernel_is_bitwise_the_general_kernel(engine, monkeypatch, N):
+    """K_A2 (csrc/pv_analyze2.cu: constant ratio >= 1; tail FFT stage in the bin threads, bin shift as a
+    scatter) against the general analysis kernel (MLX_PV_NO_KA2=1): identical output samples, peak bins,
+    f0 and phase totals -- ratios 1 (no empty bins), +3 st, +12 st (every other output bin empty), +24 st
+    (three empty bins after each), ragged batch, short chunks, a wave boundary inside a chunk."""
+    import torch
+    H = N // 4
+    xs = [S.vibrato_tone(4.0, seed=71), S.vibrato_tone(1.3, seed=72), np.zeros(700, np.float32),
+          S.two_tone(2.0)]
+    engine.use_torch_stream()
+    for semis in (0.0, 3.0, 0.37, 12.0, 24.0):
+        r = ratio(semis)
+        for env in ({}, {"MLX_PV_CHUNK": "24"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            res = []
+            for no_ka2 in ("0", "1"):
+                if no_ka2 == "1":
+                    monkeypatch.setenv("MLX_PV_NO_KA2", "1")
+                else:
+                    monkeypatch.delenv("MLX_PV_NO_KA2", raising=False)
+                engine.upload_tracks(xs)
+                out = engine.pv_run(N, H, r, wave_mib=(1 if env else -1))
+                tots = [torch.zeros(N // 2 + 1, dtype=torch.int32, device="cuda") for _ in xs]
+                engine.pv_phase_totals_dev(N, H, r, tots, wave_mib=-1)
+                torch.cuda.synchronize()
+                res.append((out, [t.cpu().numpy() for t in tots]))
+            monkeypatch.delenv("MLX_PV_NO_KA2", raising=False)
+            for k in env:
+                monkeypatch.delenv(k, raising=False)
+            (a, ta), (b, tb) = res
+            for u, v in zip(a, b):
+                assert np.array_equal(u["y"], v["y"]), (N, semis, env)
+                assert np.array_equal(u["peak"], v["peak"]) and np.array_equal(u["f0"], v["f0"]), (N, semis, env)
+            for u, v in zip(ta, tb):
+                assert np.array_equal(u, v), (N, semis, env)
+
+
 def test_per_frame_rate_array(engine, oracle):
     import torch
     x = S.vibrato_tone(2.0, seed=41)
