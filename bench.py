@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (configs[3] time-sharded, ...)")
+    ap.add_argument("--cfg3-seconds", type=float, default=7200.0, help="length of the configs[3] file")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = all this process may use)")
     return ap.parse_args()
@@ -238,6 +240,210 @@ def gen_tracks_gpu(torch, dev, ntracks, n, rank):
     return x
 
 
+def gen_long_file_gpu(torch, dev, lo, hi, seed, block=1 << 24):
+    """Samples [lo, hi) of the configs[3] synthetic channel, a closed-form function of the GLOBAL sample index
+    (so that every rank can produce its own time range and rank 0 the whole file, bit-identically):
+    8-harmonic tone, f0(t) = 220 (1 + 0.0578 sin(2 pi 0.5 t)) Hz (+-1 semitone), phase integrated in closed
+    form in float64, amplitude 0.25, plus a -50 dBFS hash-noise of the sample index."""
+    out = torch.empty(hi - lo, dtype=torch.float32, device=dev)
+    for b0 in range(lo, hi, block):
+        b1 = min(hi, b0 + block)
+        i = torch.arange(b0, b1, device=dev, dtype=torch.int64)
+        t = i.to(torch.float64) / FS
+        ph = 2 * np.pi * 220.0 * (t - (0.0578 / (2 * np.pi * 0.5)) * torch.cos(2 * np.pi * 0.5 * t))
+        sig = torch.zeros_like(t)
+        for h in range(1, 9):
+            sig += torch.sin(h * ph) / h
+        # counter-based noise: two rounds of a 64-bit mix of (index, seed) -> uniform -> centred, unit variance
+        z = i * 0x9E3779B97F4A7C1 + (seed * 0x632BE59BD9B4E019 & 0x7FFFFFFFFFFFFFFF)
+        z = (z ^ (z >> 30)) * 0x3F58476D1CE4E5B
+        z = (z ^ (z >> 27)) * 0x14D049BB133111EB
+        u = ((z ^ (z >> 31)) & 0xFFFFFF).to(torch.float64) / float(1 << 24)
+        sig = 0.25 / 1.9 * sig + (u - 0.5) * (12.0 ** 0.5) * 10.0 ** (-50.0 / 20.0)
+        out[b0 - lo:b1 - lo] = sig.to(torch.float32)
+    return out
+
+
+def cfg3_time_sharded(torch, dist, eng, dev, rank, world, seconds=7200.0, reps=3):
+    """BASELINE configs[3]: one 2 h "stereo" file (two planar mono channels), 4096-FFT / 1024-hop, +3 st,
+    sharded by contiguous time range across the ranks through mlx_pv_run_sharded_dev (NCCL seam send/recv of
+    the overlap-region samples + all-gather of the uint32 phase totals behind the C ABI, ONE analysis pass).
+    Rank 0 also runs the whole file unsharded on its own GPU: the 1-GPU time the speed-up refers to and the
+    bits the gathered sharded output must equal."""
+    from melonix_b200 import dist as D
+    N, H = 4096, 1024
+    n = int(round(seconds * FS))
+    F = (n + H - 1) // H
+    rate = semitone_ratio(SEMITONES)
+    sh = D.shard_frames(n, N, H, world, rank)
+    owns = [gen_long_file_gpu(torch, dev, sh.own_lo, sh.own_hi, 1234 + c) for c in range(2)]
+    nf = sh.frame_end - sh.frame_begin
+    outs = ([torch.empty_like(o) for o in owns], [torch.empty(nf, dtype=torch.int32, device=dev) for _ in owns],
+            [torch.empty(nf, dtype=torch.float32, device=dev) for _ in owns])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    ms_1gpu = None
+    ref = None
+    if rank == 0:   # the unsharded run (whole file on one GPU)
+        full = [gen_long_file_gpu(torch, dev, 0, n, 1234 + c) for c in range(2)]
+        ref = [torch.empty_like(f) for f in full]
+        pk = [torch.empty(F, dtype=torch.int32, device=dev) for _ in full]
+        f0 = [torch.empty(F, dtype=torch.float32, device=dev) for _ in full]
+        eng.use_torch_stream()
+        eng.upload_tracks_dev(full)
+        del full
+        eng.pv_run_dev(N, H, rate, ref, pk, f0, sample_rate=FS, wave_mib=-1)   # warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            eng.pv_run_dev(N, H, rate, ref, pk, f0, sample_rate=FS, wave_mib=-1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_1gpu = e0.elapsed_time(e1) / reps
+        del pk, f0
+    if world > 1:
+        sync_all()
+        D.run_time_sharded(eng, owns, n, N, H, rate, sample_rate=FS, outs=outs)   # warm-up: communicator, tables
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            D.run_time_sharded(eng, owns, n, N, H, rate, sample_rate=FS, outs=outs)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # bit-for-bit check on rank 0: every rank ships its owned output
+        equal = True
+        for c in range(2):
+            for r in range(world):
+                s = D.shard_frames(n, N, H, world, r)
+                if rank == 0:
+                    got = outs[0][c] if r == 0 else torch.empty(s.own_hi - s.own_lo, dtype=torch.float32, device=dev)
+                    if r != 0:
+                        dist.recv(got, r)
+                    equal = equal and bool(torch.equal(got, ref[c][s.own_lo:s.own_hi]))
+                    del got
+                elif rank == r:
+                    dist.send(outs[0][c], 0)
+        comm = getattr(eng, "_comm", None)
+        info = dict(ms=ms, frames=2 * F, frames_per_s=2 * F / (ms * 1e-3), bitwise_equal=equal,
+                    nccl_version=comm.nccl_version if comm is not None else None)
+    else:
+        info = dict(ms=ms_1gpu, frames=2 * F, frames_per_s=2 * F / (ms_1gpu * 1e-3), bitwise_equal=None)
+    if rank == 0:
+        info.update(ms_1gpu=ms_1gpu, frames_per_s_1gpu=2 * F / (ms_1gpu * 1e-3),
+                    speedup_vs_1gpu=ms_1gpu / info["ms"], n_gpus=world,
+                    workload=f"configs[3]: {seconds / 3600:.1f} h x 2 planar channels, 4096-FFT/1024-hop, +3 st, "
+                             f"time-range sharded; timed region = seam exchange + analysis + phase all-gather + synthesis",
+                    seam_floats_per_track=[N, 3 * H], phase_words_per_track=N // 2 + 1,
+                    api="mlx_pv_run_sharded_dev (NCCL inside libmelonix_b200.so)" if world > 1 else "mlx_pv_run_dev")
+    del owns, outs, ref
+    torch.cuda.empty_cache()
+    return info if rank == 0 else None
+
+
+def extras_single_gpu(torch, eng, dev, peak_gbs, nt=16, seconds=300.0):
+    """The other BASELINE configs on one GPU (secondary numbers; the headline stays configs[2]):
+    configs[0] geometry (Spec STFT 1024/256) and the FFT-size sweeps of configs[4] for the Spec path
+    (4H + 2N algorithmic bytes per frame, one batched launch over all tracks) and the PV path (8H + 8),
+    configs[1] (one 60 s track, full pitch shift)."""
+    import melonix_b200 as m
+    out = dict(tracks=nt, seconds_per_track=seconds, spec=[], pv=[])
+    n = int(seconds * FS)
+    x = gen_tracks_gpu(torch, dev, nt, n, 0)
+    eng.use_torch_stream()
+    eng.upload_tracks_dev([x[i] for i in range(nt)])
+    for N, hop in [(512, 128), (1024, 256), (2048, 512), (4096, 1024), (8192, 2048)]:
+        Fr = (n + hop - 1) // hop
+        buf = torch.empty((nt, Fr, N // 2), dtype=torch.float32, device=dev)
+        outs = [buf[i] for i in range(nt)]
+        for _ in range(2):
+            eng.spec_frames_all_dev(N, hop, outs)
+        torch.cuda.synchronize()
+        eng.profile_enable(True)
+        eng.profile_read()
+        reps = 5
+        for _ in range(reps):
+            eng.spec_frames_all_dev(N, hop, outs)
+        ms, launches = eng.profile_read()["spec"]
+        eng.profile_enable(False)
+        fps = nt * Fr * reps / (ms * 1e-3)
+        algo = 4 * hop + 2 * N
+        out["spec"].append(dict(fftN=N, hop=hop, frames_per_s=fps, algorithmic_bytes_per_frame=algo,
+                                achieved_gbs=fps * algo / 1e9, frac_of_hbm_peak=fps * algo / 1e9 / peak_gbs,
+                                kernel_ms_per_launch=ms / max(launches, 1), frames_per_launch=nt * Fr))
+        del buf, outs
+    r = semitone_ratio(SEMITONES)
+    y = torch.empty_like(x)
+    for N in (512, 1024, 2048, 4096, 8192):
+        hop = N // 4
+        Fr = (n + hop - 1) // hop
+        pk = torch.empty((nt, Fr), dtype=torch.int32, device=dev)
+        f0 = torch.empty((nt, Fr), dtype=torch.float32, device=dev)
+        o = ([y[i] for i in range(nt)], [pk[i] for i in range(nt)], [f0[i] for i in range(nt)])
+        for _ in range(2):
+            eng.pv_run_dev(N, hop, r, *o, sample_rate=FS)
+        torch.cuda.synchronize()
+        eng.profile_enable(True)
+        eng.profile_read()
+        reps = 3
+        for _ in range(reps):
+            eng.pv_run_dev(N, hop, r, *o, sample_rate=FS)
+        prof = eng.profile_read()
+        eng.profile_enable(False)
+        ms = sum(prof[k][0] for k in ("pv_analyze", "pv_scan", "pv_synth")) / reps
+        fps = nt * Fr / (ms * 1e-3)
+        algo = 8 * hop + 8
+        out["pv"].append(dict(fftN=N, hop=hop, frames_per_s=fps, algorithmic_bytes_per_frame=algo,
+                              achieved_gbs=fps * algo / 1e9, frac_of_hbm_peak=fps * algo / 1e9 / peak_gbs,
+                              kernel_ms={k: prof[k][0] / reps for k in ("pv_analyze", "pv_scan", "pv_synth")}))
+        del pk, f0
+    # configs[1]: ONE 60 s track, 2048/512 (23 MB of compulsory traffic: launch- and latency-bound)
+    n1 = 60 * FS
+    eng.upload_tracks_dev([x[0, :n1].contiguous()])
+    F1 = (n1 + HOP - 1) // HOP
+    y1 = torch.empty(n1, dtype=torch.float32, device=dev)
+    p1 = torch.empty(F1, dtype=torch.int32, device=dev)
+    g1 = torch.empty(F1, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        eng.pv_run_dev(FFT_N, HOP, r, [y1], [p1], [g1], sample_rate=FS)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        eng.pv_run_dev(FFT_N, HOP, r, [y1], [p1], [g1], sample_rate=FS)
+    e1.record()
+    torch.cuda.synchronize()
+    ms1 = e0.elapsed_time(e1) / 20
+    out["cfg1_single_60s_track"] = dict(frames=F1, ms=ms1, frames_per_s=F1 / (ms1 * 1e-3),
+                                        note="one 60 s track per call: 23 MB of traffic, three launches, latency-bound")
+    # configs[0]: the 10 s sweep, Spec STFT 1024/256 (1875 frames: a 5.8 MB job, reported for completeness)
+    n0 = 10 * FS
+    eng.upload_tracks_dev([x[0, :n0].contiguous()])
+    F0 = (n0 + 255) // 256
+    b0 = torch.empty((F0, 512), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        eng.spec_frames_dev(0, 1024, 256, 0, F0, b0)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(50):
+        eng.spec_frames_dev(0, 1024, 256, 0, F0, b0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms0 = e0.elapsed_time(e1) / 50
+    out["cfg0_spec_10s"] = dict(frames=F0, ms=ms0, frames_per_s=F0 / (ms0 * 1e-3),
+                                note="10 s, 1024-FFT/256-hop Spec STFT: one 1875-frame launch, launch-latency-bound")
+    del x, y
+    torch.cuda.empty_cache()
+    return out
+
+
 def load_traffic():
     """dram bytes per launch from the committed ncu capture (profiles/), if any."""
     p = ROOT / "profiles" / "roofline_traffic.json"
@@ -351,34 +557,65 @@ def main():
                     kernel_share={k: v / path_ms for k, v in kern_ms.items()} if path_ms else None,
                     launches_per_step={k: v[1] / args.steps for k, v in prof.items() if v[1] > 0})
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host in/out, copies timed)
-    e2e = None
+    # ---- end to end through the host-buffer C-ABI call (pinned host in/out, copies timed).  Headline `e2e`:
+    #      int16 PCM on both sides of the wire (the reference's export sink takes int16, app.cpp:1209-1212;
+    #      16-bit PCM in is x = s / 32768) -- half the bytes of the float32 form, which is reported next to it.
+    e2e = e2e_f32 = None
     if not args.no_e2e:
-        hx = torch.empty((nt, n), dtype=torch.float32, pin_memory=True)
-        hx.copy_(x)
-        hy = torch.empty((nt, n), dtype=torch.float32, pin_memory=True)
-        hp = torch.empty((nt, F), dtype=torch.int32, pin_memory=True)
-        hf = torch.empty((nt, F), dtype=torch.float32, pin_memory=True)
-        del x, y
+        del y
         torch.cuda.empty_cache()
-        ins = [hx[i] for i in range(nt)]
-        ho = ([hy[i] for i in range(nt)], [hp[i] for i in range(nt)], [hf[i] for i in range(nt)])
 
-        def estep():
-            eng.pv_process_host(ins, FFT_N, HOP, rate, ho[0], ho[1], ho[2], sample_rate=FS, wave_mib=args.wave_mib)
+        def run_e2e(dtype, steps):
+            hx = torch.empty((nt, n), dtype=dtype, pin_memory=True)
+            if dtype == torch.int16:
+                for i in range(nt):   # 16-bit PCM of the same synthetic tracks
+                    hx[i].copy_((x[i] * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+            else:
+                hx.copy_(x)
+            hy = torch.empty((nt, n), dtype=dtype, pin_memory=True)
+            hp = torch.empty((nt, F), dtype=torch.int32, pin_memory=True)
+            hf = torch.empty((nt, F), dtype=torch.float32, pin_memory=True)
+            ins = [hx[i] for i in range(nt)]
+            ho = ([hy[i] for i in range(nt)], [hp[i] for i in range(nt)], [hf[i] for i in range(nt)])
 
-        estep()  # warm-up (allocations)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            estep()
-        barrier()
-        el = max_over_ranks(time.perf_counter() - t0)
-        e2e = dict(value=world * frames_per_rank * args.e2e_steps / el, unit="frames/s",
-                   h2d_bytes_per_step=int(nt * n * 4), d2h_bytes_per_step=int(nt * n * 4 + nt * F * 8),
-                   ms_per_step=1e3 * el / args.e2e_steps, steps=args.e2e_steps,
-                   api="mlx_pv_process_host (C ABI; pinned host buffers; H2D/D2H on copy streams overlapped "
-                       "with the kernels per track)")
+            def estep():
+                eng.pv_process_host(ins, FFT_N, HOP, rate, ho[0], ho[1], ho[2], sample_rate=FS, wave_mib=args.wave_mib)
+
+            estep()  # warm-up (allocations)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                estep()
+            barrier()
+            el = max_over_ranks(time.perf_counter() - t0)
+            bps = hx.element_size()
+            fmt = "int16 PCM" if dtype == torch.int16 else "float32"
+            return dict(value=world * frames_per_rank * steps / el, unit="frames/s",
+                        h2d_bytes_per_step=int(nt * n * bps), d2h_bytes_per_step=int(nt * n * bps + nt * F * 8),
+                        ms_per_step=1e3 * el / steps, steps=steps, sample_format=f"{fmt} in, {fmt} out",
+                        api="mlx_pv_process_host_fmt (C ABI; pinned host buffers; H2D / D2H on copy streams overlapped "
+                            "with the kernels, tracks in groups of 4 per launch)")
+
+        e2e_f32 = run_e2e(torch.float32, max(1, min(2, args.e2e_steps)))
+        e2e = run_e2e(torch.int16, args.e2e_steps)
+        del x
+        torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras:
+        eng.upload_tracks([np.zeros(16, np.float32)])   # release the batch's track buffer
+        try:
+            c3 = cfg3_time_sharded(torch, dist, eng, dev, rank, world, seconds=args.cfg3_seconds)
+            if rank == 0:
+                extras["cfg3_time_sharded"] = c3
+        except Exception as e:  # noqa: BLE001  (the headline numbers above must survive a failing extra)
+            if rank == 0:
+                extras["cfg3_time_sharded"] = dict(error=f"{type(e).__name__}: {e}")
+        if world == 1:
+            try:
+                extras["other_configs"] = extras_single_gpu(torch, eng, dev, peak_gbs)
+            except Exception as e:  # noqa: BLE001
+                extras["other_configs"] = dict(error=f"{type(e).__name__}: {e}")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -395,7 +632,8 @@ def main():
                                 analysis_fft="f64", synthesis_fft="f32", phase_accumulator="u32",
                                 wave_mib=args.wave_mib, numa_binding=numa,
                                 l2="inputs and outputs (3.7 GB each per GPU) exceed the 126 MB L2; no flush needed"),
-                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
+                    clocks=clocks, e2e=e2e, e2e_f32=e2e_f32, gpu_launches=launches, roofline=roofline,
+                    cpu_baseline=cpu, extras=extras)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -85,6 +85,10 @@ MLX_API int mlx_spec_batch_dev(mlx_ctx *ctx, int track, int fftN, const int32_t 
  * [first_frame, first_frame+count).  out_dev = [count][fftN/2]. */
 MLX_API int mlx_spec_frames_dev(mlx_ctx *ctx, int track, int fftN, int hop, int64_t first_frame,
                         int64_t count, float *out_dev);
+/* The same for EVERY uploaded track in ONE launch (all F[t] = ceil(n[t] / hop) frames of track t; out_dev =
+ * host array of ntracks device pointers, out_dev[t] = [F[t]][fftN/2]): enough CTAs to fill the chip where a
+ * single track's launch lasts tens of microseconds. */
+MLX_API int mlx_spec_frames_all_dev(mlx_ctx *ctx, int fftN, int hop, float *const *out_dev);
 /* Spec + the colour ramp of SpecCache::populateTex fused (reference spec-cache.cpp:77-96):
  * out_rgb = [count][fftN/2][3] bytes, k = the brightness gain (spec-cache.cpp:79). */
 MLX_API int mlx_spec_batch_rgb(mlx_ctx *ctx, int track, int fftN, const int32_t *start_end, int count,
@@ -140,6 +144,17 @@ MLX_API int mlx_pv_synth_dev(mlx_ctx *ctx, const mlx_pv_params *p, float *const 
 MLX_API int mlx_pv_process_host(mlx_ctx *ctx, const mlx_pv_params *p, const float *const *wav,
                         const int64_t *n, int ntracks, float *const *out_wav,
                         int32_t *const *out_peak, float *const *out_f0);
+
+/* The same with a choice of sample format on each side of the PCIe wire.  MLX_FMT_I16 input: int16 PCM,
+ * x = s / 32768 (exact; what the reference's decoder makes of 16-bit audio, swr s16 -> flt, app.cpp:640-690);
+ * MLX_FMT_I16 output: int16(x * 32767.) by truncation, no clamp -- the conversion App::exportWav applies
+ * before save-wav (reference app.cpp:1209-1212), fused into the synthesis kernel, so the bytes handed to
+ * saveWav are produced on the device.  int16 on both sides halves the bytes per step.  wav[t] / out_wav[t]
+ * point at n[t] samples of the stated format. */
+typedef enum { MLX_FMT_F32 = 0, MLX_FMT_I16 = 1 } mlx_sample_format;
+MLX_API int mlx_pv_process_host_fmt(mlx_ctx *ctx, const mlx_pv_params *p, const void *const *wav, int in_format,
+                                    const int64_t *n, int ntracks, void *const *out_wav, int out_format,
+                                    int32_t *const *out_peak, float *const *out_f0);
 
 /* ---- one long file across the GPUs of a node: time-range sharding (BASELINE configs[3]) ---------
  * One rank (process or host thread) per GPU, each with its own mlx_ctx.  Rank r owns frames

@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
     L.mlx_spec_batch.argtypes = [vp, i32, i32, vp, i32, vp]
     L.mlx_spec_batch_dev.argtypes = [vp, i32, i32, vp, i32, vp]
     L.mlx_spec_frames_dev.argtypes = [vp, i32, i32, i32, i64, i64, vp]
+    L.mlx_spec_frames_all_dev.argtypes = [vp, i32, i32, C.POINTER(vp)]
     L.mlx_spec_batch_rgb.argtypes = [vp, i32, i32, vp, i32, f32, vp]
     L.mlx_pv_run.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mlx_pv_run_dev.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -108,6 +109,8 @@ def lib() -> C.CDLL:
     L.mlx_pv_run_sharded.argtypes = L.mlx_pv_run_sharded_dev.argtypes
     L.mlx_pv_process_host.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(i64), i32,
                                       C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mlx_pv_process_host_fmt.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), i32, C.POINTER(i64), i32,
+                                          C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp)]
     L.mlx_grain_render.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp]
     L.mlx_picks_levels.argtypes = [i64]
     L.mlx_picks_layout.argtypes = [i64, vp]

@@ -136,6 +136,14 @@ int layout_tracks(mlx_ctx* c, const int64_t* n, int ntracks) {
 
 int64_t num_frames(int64_t n, int hop) { return (n + hop - 1) / hop; }
 
+// K_A2 (csrc/pv_analyze2.cu) is bit-identical to the general analysis kernel but, as measured on a B200
+// (profiles/README.md), not yet faster: it runs when MLX_PV_KA2=1 (MLX_PV_NO_KA2=1 always wins).
+static bool pv_ka2_enabled() {
+  if (getenv("MLX_PV_NO_KA2")) return false;
+  const char* e = getenv("MLX_PV_KA2");
+  return e && atoi(e) != 0;
+}
+
 
 int pv_validate(mlx_ctx* c, const mlx_pv_params* p, PvPlan* pl) {
   if (!c || !p) return fail(MLX_ERR_INVALID, "null argument");
@@ -194,7 +202,7 @@ int pv_validate(mlx_ctx* c, const mlx_pv_params* p, PvPlan* pl) {
 // later would queue behind gigabytes of uploads on the single H2D copy engine.)
 
 int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* const* out_wav,
-               int32_t* const* out_peak, float* const* out_f0, PvPrepared* out) {
+               int32_t* const* out_peak, float* const* out_f0, PvPrepared* out, short* const* out_wav16) {
   const int nt = (int)c->tracks.size();
   const int H = fftN / 4, NBP = pv_nbp(fftN), NC = fftN / 2, NB = NC + 1;
   int rc = ensure_tables(c, fftN, true, &out->tb);
@@ -213,6 +221,7 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
     desc[t].n = c->tracks[t].n;
     desc[t].F = num_frames(c->tracks[t].n, H);
     desc[t].out = (synth && out_wav) ? out_wav[t] : nullptr;
+    desc[t].out16 = (synth && out_wav16) ? out_wav16[t] : nullptr;
     desc[t].peak = out_peak ? out_peak[t] : nullptr;
     desc[t].f0 = out_f0 ? out_f0[t] : nullptr;
     desc[t].rate_pf = p->rate_per_frame_dev ? p->rate_per_frame_dev[t] : nullptr;
@@ -242,7 +251,6 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
       int jn = NB;  // output bin of the next input bin (or the end of the spectrum)
       if (k + 1 < NB) jn = std::min(NB, (int)std::trunc((float)(k + 1) * r));
       const int nz = std::max(0, jn - j - 1);
-      if (nz > 15) injective = false;  // (cannot happen for rate <= 4)
       dst[k] = (uint32_t)j | ((uint32_t)nz << 16);
     }
     if (klo[0] != 0 || khi[0] != 0) injective = false;  // output bin 0 must be fed by input bin 0
@@ -250,7 +258,7 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
     const int kmax = std::max(kmin, std::min(fftN / 2, (int)std::floor(2000.0 * fftN / p->sample_rate)));
     out->scatter_ok = injective && r >= 1.0f && !p->rate_per_frame_dev && pv_analyze2_supported(fftN) &&
                       kmax - kmin + 1 <= pv_analyze2_band_capacity(fftN) && kmax < fftN / 8 &&
-                      getenv("MLX_PV_NO_KA2") == nullptr;
+                      pv_ka2_enabled();
   }
   CK(cudaMemcpyAsync(c->track_desc.p, desc, sizeof(PvTrack) * nt, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->gk.p, gk, sizeof(uint32_t) * 2 * NBP, cudaMemcpyHostToDevice, c->stream));
@@ -262,6 +270,7 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
         CK(cudaMemcpyAsync(static_cast<uint32_t*>(c->carry.p) + (size_t)t * NBP, p->phase_in_dev[t],
                            sizeof(uint32_t) * NB, cudaMemcpyDeviceToDevice, c->stream));
   }
+  out->out16 = synth && out_wav16 != nullptr;
   out->tdev = static_cast<const PvTrack*>(c->track_desc.p);
   out->carry = static_cast<uint32_t*>(c->carry.p);
   return MLX_OK;
@@ -271,7 +280,7 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
 // `first`.  Issues kernels only (plus optional D2D copies of the phase totals): nothing here touches
 // the H2D copy engine.
 //   kPvAll      K_A, scan, K_S per wave (synth = false: no K_S)
-//   kPvAnalyze  K_A + scan(carry = 0) over ONE wave; smag / lacc / tot / totc stay staged in HBM and the
+//   kPvAnalyze  K_A + scan(carry = 0) over ONE wave; the stage records / tot / totc stay resident in HBM and the
 //               carry holds the phase totals of the owned frames
 //   kPvSynth    scan(carry = phase_in) + K_S on the staged wave: the scan is re-run because the prefix of
 //               every chunk moves with the carried-in phase (it reads tot / totc only: microseconds)
@@ -289,8 +298,7 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
       return fail(MLX_ERR_STATE, "mlx_pv_synth_dev: no staged analysis with these parameters (call mlx_pv_analyze_dev first)");
   } else {
     c->staged.valid = false;  // the scratch is about to be overwritten
-    CK(c->smag.reserve(sizeof(float) * nt * rows * pl.NBP));
-    CK(c->lacc.reserve(sizeof(uint32_t) * nt * rows * pl.NBP));
+    CK(c->stage.reserve(sizeof(uint2) * nt * rows * pl.NBP));
     CK(c->tot.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
     CK(c->totc.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
     CK(c->pre.reserve(sizeof(uint32_t) * nt * nchunksA_max * pl.NBP));
@@ -300,7 +308,7 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
               static_cast<const cplx<float>*>(tb->tw_f.p),  static_cast<const cplx<float>*>(tb->twr_f.p),
               static_cast<const float*>(tb->win.p),         static_cast<const double*>(tb->win_d.p),
               static_cast<const float*>(tb->wsyn.p)};
-  PvScratch sc{static_cast<float*>(c->smag.p),    static_cast<uint32_t*>(c->lacc.p), static_cast<uint32_t*>(c->tot.p),
+  PvScratch sc{static_cast<uint2*>(c->stage.p), static_cast<uint32_t*>(c->tot.p),
                static_cast<uint32_t*>(c->totc.p), static_cast<uint32_t*>(c->pre.p),
                pr.carry + (size_t)first * pl.NBP};
   const PvTrack* tdev = pr.tdev + first;
@@ -339,7 +347,7 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
     c->launches += 1;
     if (synth && mode != kPvAnalyze) {
       c->mark(2);
-      CK(launch_pv_synth(pl.N, tdev, nt, wv, pt, sc, c->stream));
+      CK(launch_pv_synth(pl.N, tdev, nt, wv, pt, sc, pr.out16, c->stream));
       c->launches += 1;
     }
   }
@@ -369,7 +377,7 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
 int pv_execute(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, bool synth, float* const* out_wav,
                int32_t* const* out_peak, float* const* out_f0, uint32_t* const* totals_dev, PvMode mode) {
   PvPrepared pr;
-  int rc = pv_prepare(c, p, pl.N, synth, out_wav, out_peak, out_f0, &pr);
+  int rc = pv_prepare(c, p, pl.N, synth, out_wav, out_peak, out_f0, &pr, nullptr);
   if (rc) return rc;
   return pv_launch(c, p, pl, pr, 0, (int)c->tracks.size(), synth, totals_dev, mode);
 }
@@ -412,8 +420,8 @@ void mlx_destroy(mlx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&c->gk, &c->track_buf, &c->smag, &c->lacc, &c->tot, &c->totc, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
-                    &c->out_wav, &c->out_peak, &c->out_f0, &c->jobs, &c->spec_out, &c->spec_rgb, &c->g_i32a,
+  for (DevBuf* b : {&c->gk, &c->track_buf, &c->stage, &c->tot, &c->totc, &c->pre, &c->carry, &c->track_desc, &c->ptr_stage,
+                    &c->out_wav, &c->out_peak, &c->out_f0, &c->in_wav16, &c->out_wav16, &c->spec_desc, &c->jobs, &c->spec_out, &c->spec_rgb, &c->g_i32a,
                     &c->g_i32b, &c->g_f32a, &c->g_f32b, &c->g_i64, &c->g_out, &c->g_out16, &c->seg_bits,
                     &c->seg_desc, &c->seg_rows, &c->seg_count, &c->picks, &c->picks_ranges, &c->picks_out, &c->picks_desc})
     b->release();
@@ -557,6 +565,64 @@ int mlx_spec_frames_dev(mlx_ctx* c, int track, int fftN, int hop, int64_t first_
 // s0 + (i+1)*hop) with s0 a multiple of hop, which is what SpecCache::populateTex produces at a fixed
 // zoom (spec-cache.cpp:63-65) -- is handed to the kernels in regular-hop form, so that launch_spec can
 // pick the tiled kernel; any other list stays a list.
+int mlx_spec_frames_all_dev(mlx_ctx* c, int fftN, int hop, float* const* out_dev) {
+  if (!c || !out_dev) return fail(MLX_ERR_INVALID, "null argument");
+  if (c->tracks.empty()) return fail(MLX_ERR_STATE, "no tracks uploaded");
+  if (hop <= 0) return fail(MLX_ERR_INVALID, "hop must be > 0");
+  const int nt = (int)c->tracks.size();
+  // the batched launch needs the TMA-tiled regular-hop kernel (fftN <= 8192, hop a multiple of 4 and
+  // <= fftN); anything else goes track by track through the general path
+  if (fftN > 8192 || (hop & 3) != 0 || hop > fftN || getenv("MLX_SPEC_GENERIC")) {
+    for (int t = 0; t < nt; ++t) {
+      int rc = spec_common(c, t, fftN, nullptr, hop, 0, num_frames(c->tracks[t].n, hop), out_dev[t], nullptr, 0.f);
+      if (rc) return rc;
+    }
+    return MLX_OK;
+  }
+  if (!is_pow2(fftN) || fftN < 512) return fail(MLX_ERR_UNSUPPORTED, "fftN must be a power of two in [512, 32768]");
+  CK(cudaSetDevice(c->device));
+  Tables* tb = nullptr;
+  int rc = ensure_tables(c, fftN, false, &tb);
+  if (rc) return rc;
+  CK(c->spec_desc.reserve(sizeof(SpecTrackDesc) * nt));
+  mlx_ctx::Slot* slot = nullptr;
+  rc = acquire_slot(c, sizeof(SpecTrackDesc) * nt, &slot);
+  if (rc) return rc;
+  SpecTrackDesc* d = static_cast<SpecTrackDesc*>(slot->p);
+  int64_t fmax = 0;
+  int tmax = 0;
+  for (int t = 0; t < nt; ++t) {
+    d[t].x = c->track_ptr(t);
+    d[t].n = c->tracks[t].n;
+    d[t].count = num_frames(c->tracks[t].n, hop);
+    d[t].out = out_dev[t];
+    d[t].rgb = nullptr;
+    if (d[t].count > fmax) {
+      fmax = d[t].count;
+      tmax = t;
+    }
+  }
+  CK(cudaMemcpyAsync(c->spec_desc.p, d, sizeof(SpecTrackDesc) * nt, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(slot->done, c->stream));
+  SpecArgs a{};
+  a.x = c->track_ptr(tmax);  // (placeholders of the longest track: the launch geometry is sized for it)
+  a.n = c->tracks[tmax].n;
+  a.hop = hop;
+  a.first_frame = 0;
+  a.count = fmax;
+  a.out = out_dev[tmax];
+  a.tw_f = static_cast<const cplx<float>*>(tb->tw_f.p);
+  a.twr_f = static_cast<const cplx<float>*>(tb->twr_f.p);
+  a.decay = static_cast<const float*>(tb->decay.p);
+  a.multi = static_cast<const SpecTrackDesc*>(c->spec_desc.p);
+  a.ntracks = nt;
+  c->mark(3);
+  CK(launch_spec(fftN, a, c->stream));
+  c->mark(-1);
+  if (fmax > 0) c->launches += 1;
+  return MLX_OK;
+}
+
 static bool regular_run(const int32_t* se, int count, int* hop, int64_t* first_frame) {
   const int64_t h = (int64_t)se[1] - se[0];
   if (h <= 0 || se[0] < 0 || se[0] % h != 0) return false;
@@ -707,9 +773,18 @@ int mlx_pv_run(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav, int32_
   return MLX_OK;
 }
 
-int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* wav, const int64_t* n, int ntracks,
-                        float* const* out_wav, int32_t* const* out_peak, float* const* out_f0) {
+// Host buffers in, host buffers out, copies overlapped with the kernels: uploads on s_in, kernels on the
+// context stream, downloads on s_out.  Tracks go through the pipeline in groups (one K_A / scan / K_S
+// launch sequence per group: enough CTAs per launch to fill the chip, few enough tracks per group that the
+// first download starts early).  Sample formats: float32, or int16 PCM on either side -- x = s / 32768 in
+// (what the reference's decoder produces, swr s16 -> flt), int16(x * 32767.) out (the reference's export
+// conversion, app.cpp:1209-1212, fused into K_S) -- which halves the bytes on the PCIe wire.
+static int pv_process_host_impl(mlx_ctx* c, const mlx_pv_params* p, const void* const* wav, int in_fmt,
+                                const int64_t* n, int ntracks, void* const* out_wav, int out_fmt,
+                                int32_t* const* out_peak, float* const* out_f0) {
   if (!c || !p || !wav || !n || ntracks <= 0) return fail(MLX_ERR_INVALID, "bad argument");
+  if ((in_fmt != MLX_FMT_F32 && in_fmt != MLX_FMT_I16) || (out_fmt != MLX_FMT_F32 && out_fmt != MLX_FMT_I16))
+    return fail(MLX_ERR_INVALID, "sample format must be MLX_FMT_F32 or MLX_FMT_I16");
   if (p->frame_begin > 0 || p->frame_end >= 0 || p->phase_in_dev || p->rate_per_frame_dev)
     return fail(MLX_ERR_UNSUPPORTED, "mlx_pv_process_host handles whole tracks with a constant rate");
   CK(cudaSetDevice(c->device));
@@ -717,18 +792,29 @@ int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* 
   if (rc) return rc;
   const std::vector<Track> all = c->tracks;
   const int H = p->hop;
+  const bool in16 = in_fmt == MLX_FMT_I16, out16 = out_fmt == MLX_FMT_I16;
   std::vector<size_t> woff(ntracks + 1, 0), foff(ntracks + 1, 0);
   for (int t = 0; t < ntracks; ++t) {
     woff[t + 1] = woff[t] + (((size_t)n[t] + 31) & ~size_t(31));
     foff[t + 1] = foff[t] + (((size_t)num_frames(n[t], H) + 31) & ~size_t(31));
   }
-  CK(c->out_wav.reserve(sizeof(float) * std::max<size_t>(woff[ntracks], 1)));
+  if (out16)
+    CK(c->out_wav16.reserve(sizeof(short) * std::max<size_t>(woff[ntracks], 1)));
+  else
+    CK(c->out_wav.reserve(sizeof(float) * std::max<size_t>(woff[ntracks], 1)));
+  if (in16) CK(c->in_wav16.reserve(sizeof(short) * std::max<size_t>(woff[ntracks], 1)));
   CK(c->out_peak.reserve(sizeof(int32_t) * std::max<size_t>(foff[ntracks], 1)));
   CK(c->out_f0.reserve(sizeof(float) * std::max<size_t>(foff[ntracks], 1)));
   std::vector<float*> dw(ntracks, nullptr), df(ntracks, nullptr);
+  std::vector<short*> dw16(ntracks, nullptr);
   std::vector<int32_t*> dp(ntracks, nullptr);
   for (int t = 0; t < ntracks; ++t) {
-    if (out_wav && out_wav[t]) dw[t] = static_cast<float*>(c->out_wav.p) + woff[t];
+    if (out_wav && out_wav[t]) {
+      if (out16)
+        dw16[t] = static_cast<short*>(c->out_wav16.p) + woff[t];
+      else
+        dw[t] = static_cast<float*>(c->out_wav.p) + woff[t];
+    }
     if (out_peak && out_peak[t]) dp[t] = static_cast<int32_t*>(c->out_peak.p) + foff[t];
     if (out_f0 && out_f0[t]) df[t] = static_cast<float*>(c->out_f0.p) + foff[t];
   }
@@ -737,28 +823,38 @@ int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* 
   rc = pv_validate(c, p, &pl_all);
   if (rc) return rc;
   PvPrepared pr;
-  rc = pv_prepare(c, p, p->fftN, true, dw.data(), dp.data(), df.data(), &pr);
+  rc = pv_prepare(c, p, p->fftN, true, out16 ? nullptr : dw.data(), dp.data(), df.data(), &pr,
+                  out16 ? dw16.data() : nullptr);
   if (rc) return rc;
-  // scratch for the largest single track, allocated before the pipeline starts
+  // tracks per launch group
+  int grp = 4;
+  if (const char* e = getenv("MLX_PV_HOST_GROUP")) grp = std::max(1, atoi(e));
+  grp = std::min(grp, ntracks);
+  // scratch for the largest group, allocated before the pipeline starts (no cudaMalloc between launches)
   {
-    int64_t nmax = 0;
-    for (int t = 0; t < ntracks; ++t) nmax = std::max<int64_t>(nmax, n[t]);
-    c->tracks.assign(1, Track{0, nmax});
-    PvPlan pl1{};
-    rc = pv_validate(c, p, &pl1);
+    size_t rows_nbp = 0, nch_nbp = 0;
+    for (int t0 = 0; t0 < ntracks; t0 += grp) {
+      const int g = std::min(grp, ntracks - t0);
+      c->tracks.assign(all.begin() + t0, all.begin() + t0 + g);
+      PvPlan plg{};
+      rc = pv_validate(c, p, &plg);
+      if (rc) break;
+      const size_t rows = (size_t)plg.wave_frames + 3, nch = (size_t)((plg.wave_frames + 3 + plg.CA - 1) / plg.CA);
+      rows_nbp = std::max(rows_nbp, rows * plg.NBP * g);
+      nch_nbp = std::max(nch_nbp, nch * plg.NBP * g);
+    }
     c->tracks = all;
     if (rc) return rc;
-    const size_t rows = (size_t)pl1.wave_frames + 3, nch = (size_t)((pl1.wave_frames + 3 + pl1.CA - 1) / pl1.CA);
-    CK(c->smag.reserve(sizeof(float) * rows * pl1.NBP));
-    CK(c->lacc.reserve(sizeof(uint32_t) * rows * pl1.NBP));
-    CK(c->tot.reserve(sizeof(uint32_t) * nch * pl1.NBP));
-    CK(c->totc.reserve(sizeof(uint32_t) * nch * pl1.NBP));
-    CK(c->pre.reserve(sizeof(uint32_t) * nch * pl1.NBP));
+    CK(c->stage.reserve(sizeof(uint2) * rows_nbp));
+    CK(c->tot.reserve(sizeof(uint32_t) * nch_nbp));
+    CK(c->totc.reserve(sizeof(uint32_t) * nch_nbp));
+    CK(c->pre.reserve(sizeof(uint32_t) * nch_nbp));
   }
-  std::vector<cudaEvent_t> ev_in(ntracks), ev_done(ntracks);
-  for (int t = 0; t < ntracks; ++t) {
-    cudaEventCreateWithFlags(&ev_in[t], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_done[t], cudaEventDisableTiming);
+  const int ngroups = (ntracks + grp - 1) / grp;
+  std::vector<cudaEvent_t> ev_in(ngroups), ev_done(ngroups);
+  for (int g = 0; g < ngroups; ++g) {
+    cudaEventCreateWithFlags(&ev_in[g], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_done[g], cudaEventDisableTiming);
   }
   cudaEvent_t ev_zero;
   cudaEventCreate(&ev_zero);
@@ -769,34 +865,56 @@ int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* 
   if (trace)
     for (cudaEvent_t* e : {&tr_in_end, &tr_k_first, &tr_k_last, &tr_out_first, &tr_out_last}) cudaEventCreate(e);
   int result = MLX_OK;
+  // all uploads are queued first (the copy engine runs them back to back) ...
   for (int t = 0; t < ntracks && result == MLX_OK; ++t) {
-    if (n[t] > 0 &&
-        cudaMemcpyAsync(static_cast<float*>(c->track_buf.p) + all[t].offset, wav[t], sizeof(float) * n[t],
-                        cudaMemcpyHostToDevice, c->s_in) != cudaSuccess)
-      result = fail(MLX_ERR_CUDA, "H2D copy failed");
-    cudaEventRecord(ev_in[t], c->s_in);
+    if (n[t] > 0) {
+      cudaError_t e;
+      if (in16)
+        e = cudaMemcpyAsync(static_cast<short*>(c->in_wav16.p) + woff[t], wav[t], sizeof(short) * n[t],
+                            cudaMemcpyHostToDevice, c->s_in);
+      else
+        e = cudaMemcpyAsync(static_cast<float*>(c->track_buf.p) + all[t].offset, wav[t], sizeof(float) * n[t],
+                            cudaMemcpyHostToDevice, c->s_in);
+      if (e != cudaSuccess) result = fail(MLX_ERR_CUDA, "H2D copy failed");
+    }
+    if ((t + 1) % grp == 0 || t + 1 == ntracks) cudaEventRecord(ev_in[t / grp], c->s_in);
   }
   if (trace) cudaEventRecord(tr_in_end, c->s_in);
-  for (int t = 0; t < ntracks && result == MLX_OK; ++t) {
-    cudaStreamWaitEvent(c->stream, ev_in[t], 0);
-    c->tracks.assign(1, all[t]);  // plan (chunk sizes) for this track alone; kernels only from here on
+  // ... then, group by group: wait for its samples, (convert,) analyse + synthesise, download
+  for (int g = 0; g < ngroups && result == MLX_OK; ++g) {
+    const int t0 = g * grp, gn = std::min(grp, ntracks - t0);
+    cudaStreamWaitEvent(c->stream, ev_in[g], 0);
+    if (in16) {
+      for (int t = t0; t < t0 + gn && result == MLX_OK; ++t) {
+        if (launch_pcm16_to_float(static_cast<const short*>(c->in_wav16.p) + woff[t],
+                                  static_cast<float*>(c->track_buf.p) + all[t].offset, n[t], c->stream) != cudaSuccess)
+          result = fail(MLX_ERR_CUDA, "pcm16_to_float launch failed");
+        c->launches += n[t] > 0;
+      }
+      if (result) break;
+    }
+    c->tracks.assign(all.begin() + t0, all.begin() + t0 + gn);  // plan (chunk sizes) for this group; kernels only from here on
     PvPlan pl{};
     result = pv_validate(c, p, &pl);
     if (result) break;
-    result = pv_launch(c, p, pl, pr, t, 1, true, nullptr, kPvAll);
+    result = pv_launch(c, p, pl, pr, t0, gn, true, nullptr, kPvAll);
     if (result) break;
-    cudaEventRecord(ev_done[t], c->stream);
-    if (trace && t == 0) cudaEventRecord(tr_k_first, c->stream);
-    if (trace && t == ntracks - 1) cudaEventRecord(tr_k_last, c->stream);
-    cudaStreamWaitEvent(c->s_out, ev_done[t], 0);
-    const int64_t F = num_frames(n[t], H);
-    if (dw[t] && n[t] > 0) cudaMemcpyAsync(out_wav[t], dw[t], sizeof(float) * n[t], cudaMemcpyDeviceToHost, c->s_out);
-    if (dp[t] && F > 0) cudaMemcpyAsync(out_peak[t], dp[t], sizeof(int32_t) * F, cudaMemcpyDeviceToHost, c->s_out);
-    if (df[t] && F > 0) cudaMemcpyAsync(out_f0[t], df[t], sizeof(float) * F, cudaMemcpyDeviceToHost, c->s_out);
-    if (trace && t == 0) cudaEventRecord(tr_out_first, c->s_out);
-    if (trace && t == ntracks - 1) cudaEventRecord(tr_out_last, c->s_out);
+    cudaEventRecord(ev_done[g], c->stream);
+    if (trace && g == 0) cudaEventRecord(tr_k_first, c->stream);
+    if (trace && g == ngroups - 1) cudaEventRecord(tr_k_last, c->stream);
+    cudaStreamWaitEvent(c->s_out, ev_done[g], 0);
+    for (int t = t0; t < t0 + gn; ++t) {
+      const int64_t F = num_frames(n[t], H);
+      if (dw[t] && n[t] > 0) cudaMemcpyAsync(out_wav[t], dw[t], sizeof(float) * n[t], cudaMemcpyDeviceToHost, c->s_out);
+      if (dw16[t] && n[t] > 0) cudaMemcpyAsync(out_wav[t], dw16[t], sizeof(short) * n[t], cudaMemcpyDeviceToHost, c->s_out);
+      if (dp[t] && F > 0) cudaMemcpyAsync(out_peak[t], dp[t], sizeof(int32_t) * F, cudaMemcpyDeviceToHost, c->s_out);
+      if (df[t] && F > 0) cudaMemcpyAsync(out_f0[t], df[t], sizeof(float) * F, cudaMemcpyDeviceToHost, c->s_out);
+    }
+    if (trace && g == 0) cudaEventRecord(tr_out_first, c->s_out);
+    if (trace && g == ngroups - 1) cudaEventRecord(tr_out_last, c->s_out);
   }
   c->tracks = all;
+  c->staged.valid = false;
   cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->s_out),
               e3 = cudaStreamSynchronize(c->s_in);
   if (trace && result == MLX_OK) {
@@ -806,13 +924,13 @@ int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* 
     cudaEventElapsedTime(&d, ev_zero, tr_k_last);
     cudaEventElapsedTime(&e, ev_zero, tr_out_first);
     cudaEventElapsedTime(&f, ev_zero, tr_out_last);
-    fprintf(stderr, "[mlx trace] ms since start: last H2D done %.1f | kernels of track 0 done %.1f, last track %.1f | "
-                    "D2H of track 0 done %.1f, last %.1f\n", a, b, d, e, f);
+    fprintf(stderr, "[mlx trace] ms since start: last H2D done %.1f | kernels of group 0 done %.1f, last group %.1f | "
+                    "D2H of group 0 done %.1f, last %.1f\n", a, b, d, e, f);
     for (cudaEvent_t ev : {tr_in_end, tr_k_first, tr_k_last, tr_out_first, tr_out_last}) cudaEventDestroy(ev);
   }
-  for (int t = 0; t < ntracks; ++t) {
-    cudaEventDestroy(ev_in[t]);
-    cudaEventDestroy(ev_done[t]);
+  for (int g = 0; g < ngroups; ++g) {
+    cudaEventDestroy(ev_in[g]);
+    cudaEventDestroy(ev_done[g]);
   }
   cudaEventDestroy(ev_zero);
   if (result) return result;
@@ -820,6 +938,18 @@ int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* 
     return fail(MLX_ERR_CUDA, std::string("pipeline failed: ") +
                                   cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
   return MLX_OK;
+}
+
+int mlx_pv_process_host(mlx_ctx* c, const mlx_pv_params* p, const float* const* wav, const int64_t* n, int ntracks,
+                        float* const* out_wav, int32_t* const* out_peak, float* const* out_f0) {
+  return pv_process_host_impl(c, p, reinterpret_cast<const void* const*>(wav), MLX_FMT_F32, n, ntracks,
+                              reinterpret_cast<void* const*>(out_wav), MLX_FMT_F32, out_peak, out_f0);
+}
+
+int mlx_pv_process_host_fmt(mlx_ctx* c, const mlx_pv_params* p, const void* const* wav, int in_format,
+                            const int64_t* n, int ntracks, void* const* out_wav, int out_format,
+                            int32_t* const* out_peak, float* const* out_f0) {
+  return pv_process_host_impl(c, p, wav, in_format, n, ntracks, out_wav, out_format, out_peak, out_f0);
 }
 
 // ------------------------------------------------------------------------------------------------ grains

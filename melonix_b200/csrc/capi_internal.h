@@ -91,9 +91,10 @@ struct mlx_ctx {
   std::map<int, mlx::Tables> tables;
 
   // phase-vocoder scratch
-  mlx::DevBuf smag, lacc, tot, totc, pre, carry, track_desc, ptr_stage, gk;
+  mlx::DevBuf stage, tot, totc, pre, carry, track_desc, ptr_stage, gk;
   mlx::DevBuf out_wav, out_peak, out_f0;  // device results for the host-pointer entry points
-  mlx::DevBuf jobs, spec_out, spec_rgb;
+  mlx::DevBuf in_wav16, out_wav16;        // int16 PCM staging of mlx_pv_process_host_fmt
+  mlx::DevBuf jobs, spec_out, spec_rgb, spec_desc;
   mlx::DevBuf g_i32a, g_i32b, g_f32a, g_f32b, g_i64, g_out, g_out16;
   mlx::DevBuf seg_bits, seg_desc, seg_rows, seg_count;  // grain segmentation scratch
   mlx::DevBuf picks, picks_ranges, picks_out, picks_desc;  // min/max pyramid of track `picks_track` + query staging
@@ -108,7 +109,7 @@ struct mlx_ctx {
   Slot slots[8];
   int next_slot = 0;
 
-  // analysis left staged by mlx_pv_analyze_dev (K_A output resident in smag / lacc / tot / totc)
+  // analysis left staged by mlx_pv_analyze_dev (K_A output resident in stage / tot / totc)
   struct Staged {
     bool valid = false;
     int N = 0, first = 0, nt = 0, CA = 0;
@@ -127,6 +128,7 @@ struct PvPrepared {
   uint32_t* carry = nullptr;      // [ntracks][NBP]
   Tables* tb = nullptr;
   bool scatter_ok = false;        // the constant-rate pitch-up analysis kernel (K_A2) applies
+  bool out16 = false;             // K_S writes PvTrack::out16 (int16 PCM) instead of PvTrack::out
 };
 
 enum PvMode { kPvAll = 0, kPvAnalyze = 1, kPvSynth = 2 };
@@ -140,6 +142,6 @@ int layout_tracks(mlx_ctx* c, const int64_t* n, int ntracks);
 int64_t num_frames(int64_t n, int hop);
 int pv_validate(mlx_ctx* c, const mlx_pv_params* p, PvPlan* pl);
 int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* const* out_wav,
-               int32_t* const* out_peak, float* const* out_f0, PvPrepared* out);
+               int32_t* const* out_peak, float* const* out_f0, PvPrepared* out, short* const* out_wav16);
 
 }  // namespace mlx

@@ -18,6 +18,8 @@ struct PvTrack {
   long long n;             // samples
   long long F;             // frames = ceil(n / hop)
   float* out;              // [n] or nullptr
+  short* out16;            // [n] or nullptr: the output as the reference's export sink takes it,
+                           // int16(x * 32767.) by truncation, no clamp (app.cpp:1209-1212)
   int* peak;               // [F] or nullptr
   float* f0;               // [F] or nullptr
   const float* rate_pf;    // [F] or nullptr
@@ -55,8 +57,8 @@ struct PvWave {
 };
 
 struct PvScratch {
-  float* smag;      // [ntracks][rows][NBP]  shifted magnitudes
-  uint32_t* lacc;   // [ntracks][rows][NBP]  chunk-local inclusive phase sums
+  uint2* stage;     // [ntracks][rows][NBP]  per output bin: .x = shifted magnitude (float bits), .y = chunk-local
+                    //                       inclusive phase sum -- one 8-byte record, one store in K_A, one load in K_S
   uint32_t* tot;    // [ntracks][nchunksA][NBP] chunk totals over all frames of the chunk
   uint32_t* totc;   // [ntracks][nchunksA][NBP] chunk totals over its frames < we (carry to the next wave)
   uint32_t* pre;    // [ntracks][nchunksA][NBP] exclusive prefix (incl. carry)
@@ -74,8 +76,11 @@ cudaError_t launch_pv_analyze(int fftN, const PvTrack* tracks_dev, int ntracks, 
                               const PvTables& tb, const PvScratch& sc, cudaStream_t st);
 cudaError_t launch_pv_scan(int fftN, int ntracks, const PvWave& wv, const PvScratch& sc,
                            cudaStream_t st);
+// out16: write PvTrack::out16 (int16) instead of PvTrack::out (float)
 cudaError_t launch_pv_synth(int fftN, const PvTrack* tracks_dev, int ntracks, const PvWave& wv,
-                            const PvTables& tb, const PvScratch& sc, cudaStream_t st);
+                            const PvTables& tb, const PvScratch& sc, bool out16, cudaStream_t st);
+// int16 PCM -> float samples x = s / 32768 (exact; what the reference's decoder hands to App, swr s16 -> flt)
+cudaError_t launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t st);
 cudaError_t pv_configure(int fftN);  // cudaFuncSetAttribute for the instantiation
 // K_A2 (pv_analyze2.cu): constant rate >= 1, fftN in {1024, 2048}; bit-identical to launch_pv_analyze
 bool pv_analyze2_supported(int fftN);
@@ -86,6 +91,14 @@ cudaError_t launch_pv_analyze2(int fftN, const PvTrack* tracks_dev, int ntracks,
                                const PvTables& tb, const PvScratch& sc, cudaStream_t st);
 
 // ---- Spec
+// per-track part of a batched regular-hop launch (blockIdx.y = track): overrides x / n / count / out / rgb
+struct SpecTrackDesc {
+  const float* x;
+  long long n;
+  long long count;
+  float* out;
+  unsigned char* rgb;
+};
 struct SpecArgs {
   const float* x;       // sample 0 of the padded device copy
   long long n;
@@ -99,6 +112,8 @@ struct SpecArgs {
   const cplx<float>* tw_f;
   const cplx<float>* twr_f;
   const float* decay;   // decay[d] = expf(-2.5e-4f * d), d in [0, fftN] (host glibc expf, spec.cpp:58)
+  const SpecTrackDesc* multi;  // nullptr, or [ntracks] (device): one launch over every track, regular hop only
+  int ntracks;
 };
 cudaError_t spec_configure(int fftN);
 cudaError_t launch_spec(int fftN, const SpecArgs& a, cudaStream_t st);

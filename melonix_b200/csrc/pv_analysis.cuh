@@ -72,14 +72,18 @@ MLX_HD float atan2_abs(float ay, float x) {
 // is exact integer arithmetic.  The only discontinuous decision -- on which side of the +-pi cut d
 // lies -- is taken from the sign of Im(X conj(Xprev) (-i)^bin) evaluated in DOUBLE; when the
 // integer difference landed on the other side, `flip` tells the consumer to add -+2^32.
-MLX_HD void analysis_bin(double a, double b, double c, double d, uint32_t& p_prev,
-                                             float& mag_prev, int bin, bool real_bin, float& mag, int& d32,
-                                             bool& flip) {
+// step 1 of analysis_bin: the frame's own magnitude and integer-turn phase (no dependence on the previous frame)
+MLX_HD void analysis_polar(double a, double b, float& mag, uint32_t& P) {
   const float af = (float)a, bf = (float)b;
   mag = fast_sqrt(fmaf(af, af, bf * bf));
   const float pabs = atan2_abs(fabsf(bf), af);
-  uint32_t P = pv_f2u_rn(pabs * 683565275.5764316f);  // 2^32 / (2 pi); pabs <= pi -> <= 2^31
+  P = pv_f2u_rn(pabs * 683565275.5764316f);  // 2^32 / (2 pi); pabs <= pi -> <= 2^31
   P = (pv_f2bits(bf) >> 31) ? (0u - P) : P;
+}
+
+// step 2: the wrapped phase advance against the previous frame (X_prev = (c, d), its phase and magnitude)
+MLX_HD void analysis_advance(double a, double b, double c, double d, uint32_t P, uint32_t p_prev, float mag,
+                             float mag_prev, int bin, bool real_bin, int& d32, bool& flip) {
   d32 = (int)(P - p_prev - ((uint32_t)bin << 30));
   const bool gate = mag * mag_prev <= 1e-18f;  // silence gate |Z| <= 1e-18 -> d = 0
   const unsigned dneg = (unsigned)d32 >> 31;
@@ -97,6 +101,14 @@ MLX_HD void analysis_bin(double a, double b, double c, double d, uint32_t& p_pre
     flip = dneg != sbit;
   }
   d32 = gate ? 0 : d32;
+}
+
+MLX_HD void analysis_bin(double a, double b, double c, double d, uint32_t& p_prev,
+                                             float& mag_prev, int bin, bool real_bin, float& mag, int& d32,
+                                             bool& flip) {
+  uint32_t P;
+  analysis_polar(a, b, mag, P);
+  analysis_advance(a, b, c, d, P, p_prev, mag, mag_prev, bin, real_bin, d32, flip);
   p_prev = P;
   mag_prev = mag;
 }

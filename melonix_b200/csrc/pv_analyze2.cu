@@ -4,33 +4,35 @@
 // path for ratios < 1, per-frame ratios and the other transform sizes.
 //
 // What is different, and why (round-1 ncu: the shared-memory data pipe was the busiest unit of K_A, 62 %,
-// with 23 % of its wavefronts bank conflicts; 49 % issue-slot utilisation behind three CTA-wide barriers
-// per batch):
+// with 23 % of its wavefronts bank conflicts):
 //
 //  * The LAST FFT stage moves from the FFT threads to the threads that own the bins.  The Stockham plan of
-//    the N/2-point transform is 16 x 16 x R (R = 2, 4, 8 for fftN = 1024, 2048, 4096): the frame's FFT group
-//    runs the two radix-16 stages and leaves 256-point sub-transforms in shared memory; the radix-R
-//    butterfly j produces bins j + 256 d, its mirror butterfly 256 - j produces exactly the mirrored bins
+//    the N/2-point transform is 16 x 16 x R (R = 2, 4 for fftN = 1024, 2048): the frame's FFT group runs the
+//    two radix-16 stages and leaves 256-point sub-transforms in shared memory; the radix-R butterfly j
+//    produces bins j + 256 d, its mirror butterfly 256 - j produces exactly the mirrored bins
 //    N/2 - (j + 256 d).  Two lanes of one warp (lane, lane ^ 16) take the two butterflies and swap half of
 //    their outputs with warp shuffles, after which each holds R/2 complete (k, N/2 - k) pairs in registers.
 //    Gone: the last-stage load, the natural-order store, the pair-phase loads (3 x 16 KB per frame of
 //    16-byte shared-memory traffic at fftN = 2048) and one group barrier.
-//  * Bin shift as a SCATTER from the thread that analysed the bin.  For a ratio >= 1 the map
-//    k -> j = trunc(float(k) * r) is injective, so the thread that owns input bin k owns output bin j (and
-//    the empty output bins up to the next one) for the whole launch: the exact phase increment, the running
-//    phase and the two global stores happen right where magnitude and phase advance were computed.  Gone:
-//    the (mag, d) records in shared memory (8-byte accesses at a 16-byte stride: all of the kernel's bank
-//    conflicts), the gather phase and its CTA-wide barrier.  Input bins whose output bin lies beyond the
-//    Nyquist bin are not analysed at all (16 % of the bins at +3 semitones).
+//  * The (magnitude, phase advance) records of a pair go back, as ONE 16-byte store, into the slot the
+//    thread itself loaded its butterfly input from (nobody else reads that slot): record of bin k < N/4 in
+//    the first half of slot k, of bin N/2 - k in the second half.  No 8-byte stores at a 16-byte stride (the
+//    general kernel's bank conflicts), no extra shared memory.
 //  * The stage-1 output is stored LINEARLY (stage-1 stores and the tail loads are unit-stride, for the
 //    mirrored butterflies at any alignment): conflict-free without padding.  Only the stage-0 exchange
 //    keeps the padded layout of fft.cuh.
+//  * Bins 0, N/2 (real) and N/4 (self-mirrored) are left over by the pairing; analysing them in thread 0
+//    would make warp 0 the straggler of every bin phase.  Thread 0 parks Z[0] and Z[N/4] in shared memory
+//    and a warp that idles after the barrier takes them, one lane per frame, writing their output bins
+//    directly (for a ratio >= 1 every output bin is fed by at most one input bin).
 //  * One TMA tile buffer instead of two: the refill is issued as soon as the FFT groups have taken their
 //    samples out and lands under the (long) bin phase.
+//  * The phase increment uses inc = A + ((d r + 2^25) >> 26) + flip term with the 32-bit per-bin constant
+//    A = 16 k r mod 2^32 (the same value as pv_shift.cuh's 64-bit base form: r k 2^30 is a multiple of 2^26).
 //
 // Per batch of G frames: [TMA wait] FFT stages 0-1 | __syncthreads | tail butterflies, pair split,
-// magnitude / integer-turn phase / FP64 cut decision, scatter | __syncthreads | peak bin + f0 (one warp per
-// frame).  Two CTA-wide barriers (three before).
+// magnitude / integer-turn phase / FP64 cut decision, records | __syncthreads | bin shift (gather) with
+// coalesced 8-byte stores, Nyquist output bin, peak bin + f0, left-over bins | __syncthreads.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -68,10 +70,11 @@ struct Ka2Cfg {
   static constexpr int BUF = P::BUF;       // padded complex slots per frame (stage-0 exchange)
   static constexpr int TILE = N + (G - 1) * H;
   static constexpr int SLOTS = R / 2;      // (k, N/2 - k) pairs per thread
-  static constexpr int PKB = N / 16;       // capacity of the peak-search band [kmin, kmax]
+  static constexpr int QB = NC / THREADS;  // output bins per thread in the gather (bin NC: last warp)
+  static constexpr int ZSLOT = BUF - 1;    // an all-zero record (what an empty K_j reads); the padded exchange ends at BUF - 2
   static constexpr bool WIN_D = (N <= 2048);
   static constexpr size_t SMEM = sizeof(cplx<double>) * G * BUF + (WIN_D ? sizeof(double) * N : 0) +
-                                 sizeof(float) * TILE + 8 * G * PKB + 16;
+                                 sizeof(float) * TILE + sizeof(cplx<double>) * 2 * G + 16;
 };
 
 // the FFT role's only twiddle register (shape expected by Fft<>::compute)
@@ -80,19 +83,16 @@ struct Ka2Twiddle {
   cplx<double> w[1];
 };
 
-// what the scatter needs to know about one input bin, decoded from PvWave::dst[k]
-struct BinDst {
-  int j;        // output bin, -1: beyond the Nyquist bin (the input bin is dropped)
-  int nz;       // empty output bins j+1 .. j+nz that follow (they belong to this bin's owner)
-  unsigned long long base;  // r_fix * k * 2^30 + 2^25 (pv_shift.cuh)
-};
-__device__ __forceinline__ BinDst make_bin_dst(const uint32_t* __restrict__ dst, int k, uint32_t r_fix) {
-  const uint32_t e = __ldg(dst + k);
-  BinDst b;
-  b.j = (e == 0xffffffffu) ? -1 : (int)(e & 0xffffu);
-  b.nz = (e == 0xffffffffu) ? 0 : (int)(e >> 16);
-  b.base = (unsigned long long)r_fix * ((unsigned long long)k << 30) + (1ULL << 25);
-  return b;
+// inc of one frame for an output bin whose source record is (mag bits with the cut-flip flag in the sign,
+// d): (A + ((d * r_fix + 2^25) >> 26) + flip term) mod 2^32, A = 16 * kh * r_fix mod 2^32 -- the value of
+// pv_shift.cuh's shift_inc (base = r_fix * kh * 2^30 + 2^25 is A * 2^26 + 2^25 mod 2^64; the flip term
+// -+r_fix * 2^32 is -+64 r_fix after the shift).  An empty K_j reads the zero record with A = (j & 3) << 30.
+__device__ __forceinline__ uint32_t shift_inc_a(uint32_t A, int d, uint32_t mb, int r_fix) {
+  long long B;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(B) : "r"(d), "r"(r_fix), "l"(1LL << 25));
+  const uint32_t q = __funnelshift_r((uint32_t)B, (uint32_t)((unsigned long long)B >> 32), 26);
+  const int adj = ((int)mb >> 31) & (d < 0 ? (r_fix << 6) : -(r_fix << 6));
+  return A + q + (uint32_t)adj;
 }
 
 // running state of one analysed bin across the frames of a chunk
@@ -100,28 +100,44 @@ struct BinState {
   cplx<double> x;   // previous frame's spectrum value (for the FP64 decision at the +-pi cut)
   uint32_t p;       // previous frame's phase, integer turns
   float mag;        // previous frame's magnitude (silence gate)
-  uint32_t lacc;    // chunk-local running synthesis phase of the output bin
 };
+
+// exp(-2 pi i (bj + 256 s) / N) from w0 = exp(-2 pi i bj / N): a rotation by the constant angle
+// -2 pi 256 s / N (N = 2048: s = 1 -> -pi/4; N = 4096: -pi/8 steps), 4 FP64 operations instead of registers
+// trunc(float(k) * r) with a plain float multiply, exactly as the spec (A.5) and the oracle do
+__device__ __forceinline__ int shift_bin_ka2(int k, float r) { return (int)truncf(__fmul_rn((float)k, r)); }
+
+template <int N>
+__device__ __forceinline__ cplx<double> pair_twiddle(const cplx<double> w0, int s) {
+  if (s == 0) return w0;
+  // cmul_w16<-1, M>: multiply by exp(-2 pi i M / 16); 256 s / N turns = (4096 s / N) sixteenths
+  constexpr int STEP = 4096 / N;  // N = 2048 -> 2, N = 4096 -> 1 (N = 1024 has one slot)
+  switch (s * STEP) {
+    case 1: return cmul_w16<-1, 1>(w0);
+    case 2: return cmul_w16<-1, 2>(w0);
+    case 3: return cmul_w16<-1, 3>(w0);
+    default: return w0;
+  }
+}
 
 template <int N>
 __global__ void __launch_bounds__(Ka2Cfg<N>::THREADS, MLX_KA2_CTAS)
 pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = Ka2Cfg<N>;
-  using P = typename Cfg::P;
   constexpr int NC = Cfg::NC, R = Cfg::R, NQ = Cfg::NQ, TPF = Cfg::TPF, G = Cfg::G, H = Cfg::H;
   constexpr int NB = Cfg::NB, NBP = Cfg::NBP, BUF = Cfg::BUF, TILE = Cfg::TILE, SLOTS = Cfg::SLOTS;
-  constexpr int THREADS = Cfg::THREADS, PKB = Cfg::PKB;
+  constexpr int THREADS = Cfg::THREADS, QB = Cfg::QB, ZSLOT = Cfg::ZSLOT;
   constexpr bool WD = Cfg::WIN_D;
   using C = cplx<double>;
   using F = Fft<double, NC, -1>;
+  static_assert(G <= 8, "the left-over bins use one lane per frame of an 8-lane subgroup");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   C* buf = reinterpret_cast<C*>(smem_raw);                        // [G][BUF]
   double* s_win = reinterpret_cast<double*>(buf + G * BUF);       // [N] when WD
   float* tile = reinterpret_cast<float*>(s_win + (WD ? N : 0));   // [TILE]
-  float* pk_mag = tile + TILE;                                    // [G][PKB] magnitudes of the search band (sign = cut flip)
-  int* pk_d = reinterpret_cast<int*>(pk_mag + G * PKB);           // [G][PKB] their wrapped phase advance
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(pk_d + G * PKB);
+  C* s_sp = reinterpret_cast<C*>(tile + TILE);                    // [G][2] Z[0] and Z[NC/2] of each frame
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_sp + 2 * G);
 
   const int tid = threadIdx.x;
   const PvTrack tr = tracks[blockIdx.y];
@@ -142,6 +158,7 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
   if constexpr (WD) {
     for (int i = tid; i < N; i += THREADS) s_win[i] = tb.win_d[i];
   }
+  if (tid < G) buf[tid * BUF + ZSLOT] = C{0.0, 0.0};  // the zero record of every frame buffer (never overwritten)
   __syncthreads();  // mbarrier initialised, window staged
   if (tid == 0) {   // first tile: samples [(a-1-3)H, (a-1+G)H) of the zero-padded track
     mbar_expect_tx(mbar, TILE * sizeof(float));
@@ -154,100 +171,98 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
   tw1.w[0] = tb.tw_d[(t & 15) * (NC / 256)];
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
 
-  // ---- bin role: lanes (l, l ^ 16) of a warp share the butterfly pair (j, 256 - j)
+  // ---- pair role: lanes (l, l ^ 16) of a warp share the butterfly pair (j, 256 - j)
   const int warp = tid >> 5, lane = tid & 31, hside = lane >> 4;
   const int ju = warp * 16 + (lane & 15);             // unit, 0 .. 127
   const bool special = (ju == 0);                     // butterflies 0 and 128 mirror onto themselves
   const int bj = special ? (hside ? NQ / 2 : 0) : (hside ? NQ - ju : ju);
   const C wtail = tb.tw_d[bj];                        // exp(-2 pi i bj / NC): twiddle of tail butterfly bj
-  const uint32_t r_fix = (uint32_t)wv.r_fix;
-  // slot s: bins kS = bj + 256 s and NC - kS.  Thread 0 (bj = 0): slot 0 = the real bins 0 and NC, slots
-  // s >= 1 = (256 s, NC - 256 s) from its own outputs, plus the self-mirrored bin NC/2 (extra state).
-  C wpair[SLOTS];
+  const int r_fix = (int)wv.r_fix;
+  // slot s: bins kS = bj + 256 s < NC/2 and NC - kS.  Thread 0 (bj = 0): its slot 0 would be the real bins
+  // 0 and NC, and bin NC/2 (from Z[NC/2], its output R/2) pairs with itself: those three are the left-over
+  // bins (see the header); slots s >= 1 of thread 0 pair its own outputs s and R - s.
+  const C wpair0 = tb.twr_d[bj];  // exp(-2 pi i bj / N); slot s uses exp(-2 pi i (bj + 256 s) / N) = wpair0 * rot_s
   BinState sk[SLOTS], sm[SLOTS];
-  BinDst dk[SLOTS], dm[SLOTS];
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
-    const int k = bj + NQ * s;
-    wpair[s] = tb.twr_d[k];  // exp(-2 pi i k / N), k <= NC/2
-    dk[s] = make_bin_dst(wv.dst, k, r_fix);
-    dm[s] = make_bin_dst(wv.dst, NC - k, r_fix);
-    sk[s] = BinState{C{1.0, 0.0}, 0u, 1.f, 0u};  // frame -1 has phi = 0 <=> X = 1
+    sk[s] = BinState{C{1.0, 0.0}, 0u, 1.f};  // frame -1 has phi = 0 <=> X = 1
     sm[s] = sk[s];
   }
-  BinState sself{C{1.0, 0.0}, 0u, 1.f, 0u};  // bin NC/2 (thread 0 only)
-  const BinDst dself = make_bin_dst(wv.dst, NC / 2, r_fix);
-  const int kmin = wv.kmin, kmax = wv.kmax;
-  const size_t row0 = (size_t)blockIdx.y * wv.rows;
-  uint32_t emitted = 0u;  // frames of this chunk that have emitted so far (empty output bins advance by j/4 turn each)
 
-  // one analysed bin -> its output bin j (+ the empty bins that follow): exact phase increment, running
-  // phase, two global stores.  `mb` = magnitude bits with the cut-flip flag in the sign bit.
-  auto scatter = [&](const BinDst& d, BinState& st, float mag, int dq, bool flip, float* rs, uint32_t* rl) {
-    if (d.j < 0) return;
-    const uint32_t mb = __float_as_uint(mag) | (flip ? 0x80000000u : 0u);
-    st.lacc += shift_inc(d.base, dq, mb, (int)r_fix);
-    rs[d.j] = mag;
-    rl[d.j] = st.lacc;
-    for (int z = 1; z <= d.nz; ++z) {  // empty K_j: smag = 0, s_nu = j -> inc = frac(j / 4) per frame
-      rs[d.j + z] = 0.f;
-      rl[d.j + z] = (emitted * (uint32_t)((d.j + z) & 3)) << 30;
+  // ---- left-over bins: warp `spw`, 8-lane subgroup = bin (NC/2, 0, NC), lane within it = frame
+  const int spw = G % (THREADS / 32);
+  const int spk = (lane >> 3) == 0 ? NC / 2 : ((lane >> 3) == 1 ? 0 : NC);
+  const bool sp_lane = warp == spw && lane < 24;
+  const bool sp_owner = sp_lane && (lane & 7) == 0;  // the lane that reports the subgroup's totals
+  const int spj = shift_bin_ka2(spk, wv.rate);        // the output bin this input bin feeds (if <= NC)
+  const bool sp_fed = sp_lane && spj <= NC;
+  const uint32_t spA = ((uint32_t)spk * (uint32_t)r_fix) << 4;
+  BinState ssp{C{1.0, 0.0}, 0u, 1.f};
+  uint32_t sp_lacc = 0u;
+
+  // ---- gather role: output bins j = tid + 256 q (and bin NC: the last warp, one lane per frame)
+  //   goff: byte offset of the source record inside a frame buffer (0xffffffff: fed by a left-over bin,
+  //   written by the `spw` lanes);  gA: the per-bin constant of shift_inc_a
+  auto source_of = [&](int j, uint32_t& off, uint32_t& A) {
+    const uint32_t kk = __ldg(wv.gk + j);
+    const int klo = (int)(kk & 0xffffu), kh = (int)(kk >> 16);
+    if (klo > kh) {  // empty K_j: smag = 0, s_nu = j -> inc = frac(j / 4) turn per frame
+      off = 16u * ZSLOT;
+      A = ((uint32_t)j & 3u) << 30;
+    } else if (kh == 0 || kh == NC / 2 || kh == NC) {
+      off = 0xffffffffu;
+      A = 0u;
+    } else {
+      off = kh < NC / 2 ? 16u * kh : 16u * (NC - kh) + 8u;
+      A = ((uint32_t)kh * (uint32_t)r_fix) << 4;
     }
   };
-  // phase totals of the chunk's output bins (`cnt` frames emitted): tot / totc rows
-  auto put_total = [&](uint32_t* row, const BinDst& d, const BinState& st, uint32_t cnt) {
-    if (d.j < 0) return;
-    row[d.j] = st.lacc;
-    for (int z = 1; z <= d.nz; ++z) row[d.j + z] = (cnt * (uint32_t)((d.j + z) & 3)) << 30;
-  };
-  auto put_totals = [&](uint32_t* row, uint32_t cnt) {
+  uint32_t goff[QB], gA[QB], lacc[QB], totc[QB];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      put_total(row, dk[s], sk[s], cnt);
-      if (!(special && !hside && s == 0) || true) put_total(row, dm[s], sm[s], cnt);
-    }
-    if (tid == 0) put_total(row, dself, sself, cnt);
-  };
+  for (int q = 0; q < QB; ++q) {
+    source_of(tid + q * THREADS, goff[q], gA[q]);
+    lacc[q] = totc[q] = 0u;
+  }
+  uint32_t noff, nA, lacc_nyq = 0u, totc_nyq = 0u;
+  source_of(NC, noff, nA);
+
+  const int kmin = wv.kmin, kmax = wv.kmax;
+  uint2* const stage_t = sc.stage + (size_t)blockIdx.y * wv.rows * NBP;  // this track's rows of the wave
+  const int we_rel = (int)min(wv.we - a, (long long)0x3fffffff);  // frames >= a + we_rel lie past the wave end
+  const int b_rel = (int)(b - a);
 
   for (int bi = 0; bi < nbatch; ++bi) {
-    const long long f_first = a - 1 + (long long)bi * G;
+    const int f_rel = bi * G - 1;                       // first frame of the batch, relative to a
+    const long long f_first = a + f_rel;
     mbar_wait(mbar, bi & 1);
 
     // ---- FFT role: window, radix-16 stage 0 -> padded exchange -> radix-16 stage 1 -> linear store
-    {
-      const long long fg = f_first + g;
-      if (fg >= 0 && fg < b) {
-        C x[16];
-        const float* src = tile + g * H;
+    if (f_first + g >= 0 && f_rel + g < b_rel) {
+      C x[16];
+      const float* src = tile + g * H;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          const int i = t + m * TPF;
-          const float2 s2 = *reinterpret_cast<const float2*>(src + 2 * i);
-          if constexpr (WD) {
-            const double2 w2 = *reinterpret_cast<const double2*>(s_win + 2 * i);
-            x[m] = C{w2.x * (double)s2.x, w2.y * (double)s2.y};
-          } else {
-            const float2 w2 = __ldg(reinterpret_cast<const float2*>(tb.win + 2 * i));
-            x[m] = C{(double)w2.x * (double)s2.x, (double)w2.y * (double)s2.y};
-          }
-        }
-        C* fb = buf + g * BUF;
-        F::template compute<0>(x, fb, t, tw1);
-        bar.sync();
-        F::load(x, fb, t);
-        bar.sync();  // every load of the group done before the linear stores overwrite the padded slots
-        {
-          C v[16];
-#pragma unroll
-          for (int r = 0; r < 16; ++r) v[r] = x[r];
-          twiddle_powers<16>(v, tw1.w[0]);
-          dft16<-1>(v);
-          const int k = t & 15;
-          C* p = fb + (t - k) * 16 + k;  // stage-1 butterfly t writes elements (t-k)*16 + k + 16 r
-#pragma unroll
-          for (int r = 0; r < 16; ++r) p[r * 16] = v[r];
+      for (int m = 0; m < 16; ++m) {
+        const int i = t + m * TPF;
+        const float2 s2 = *reinterpret_cast<const float2*>(src + 2 * i);
+        if constexpr (WD) {
+          const double2 w2 = *reinterpret_cast<const double2*>(s_win + 2 * i);
+          x[m] = C{w2.x * (double)s2.x, w2.y * (double)s2.y};
+        } else {
+          const float2 w2 = __ldg(reinterpret_cast<const float2*>(tb.win + 2 * i));
+          x[m] = C{(double)w2.x * (double)s2.x, (double)w2.y * (double)s2.y};
         }
       }
+      C* fb = buf + g * BUF;
+      F::template compute<0>(x, fb, t, tw1);
+      bar.sync();
+      F::load(x, fb, t);
+      bar.sync();  // every load of the group done before the linear stores overwrite the padded slots
+      twiddle_powers<16>(x, tw1.w[0]);
+      dft16<-1>(x);
+      const int k = t & 15;
+      C* p = fb + (t - k) * 16 + k;  // stage-1 butterfly t writes elements (t-k)*16 + k + 16 r
+#pragma unroll
+      for (int r = 0; r < 16; ++r) p[r * 16] = x[r];
     }
     __syncthreads();  // sub-transforms of all frames in place; the tile has been consumed
     if (tid == 0 && bi + 1 < nbatch) {
@@ -256,99 +271,171 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
       tma_load_1d(tile, tr.x + (f_first + G - 3) * H, TILE * sizeof(float), mbar);
     }
 
-    // ---- bin role
-    const int g_hi = (int)min((long long)G, b - f_first);  // frames of this batch that exist: [g_lo, g_hi)
+    // ---- pair role: tail butterfly, mirrored partner by shuffle, pair split, analysis, records
+    const int g_hi = min(G, b_rel - f_rel);  // frames of this batch that exist: [g_lo, g_hi)
     const int g_lo = f_first < 0 ? 1 : 0;
 #pragma unroll(kKa2Unroll)
-    for (int gg = 0; gg < G; ++gg) {
-      if (gg >= g_hi) break;
-      if (gg < g_lo) continue;
-      const long long ff = f_first + gg;
-      const bool emit = (bi != 0 || gg != 0);  // the chunk's leading halo frame only seeds the state
-      const C* zb = buf + gg * BUF + bj;
+    for (int gg = g_lo; gg < g_hi; ++gg) {
+      C* zb = buf + gg * BUF + bj;
       C v[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = zb[r * NQ];
       twiddle_powers<R>(v, wtail);
       dft_r<R, -1>(v);  // v[d] = Z[bj + 256 d]
-      // mirrored partners: slot s pairs Z[bj + 256 s] with the other lane's Z[(256 - bj) + 256 (R-1-s)]
-      C zc[SLOTS];
-#pragma unroll
-      for (int s = 0; s < SLOTS; ++s) {
-        const C mine = v[R - 1 - s];
-        C got;
-        got.x = __shfl_xor_sync(0xffffffffu, mine.x, 16);
-        got.y = __shfl_xor_sync(0xffffffffu, mine.y, 16);
-        // the self-mirrored butterflies: 128 pairs its outputs d <-> R-1-d, 0 pairs d <-> R-d
-        zc[s] = special ? (hside ? mine : v[(R - s) % R]) : got;
+      if (tid == 0) {
+        s_sp[2 * gg] = v[0];
+        s_sp[2 * gg + 1] = v[R / 2];
       }
-      if (emit) ++emitted;
-      float* rs = sc.smag + (row0 + (size_t)(ff - wv.wb)) * NBP;
-      uint32_t* rl = sc.lacc + (row0 + (size_t)(ff - wv.wb)) * NBP;
 #pragma unroll
       for (int s = 0; s < SLOTS; ++s) {
+        // slot s pairs Z[bj + 256 s] with the other lane's Z[(256 - bj) + 256 (R-1-s)]; the self-mirrored
+        // butterflies pair their own outputs: 128 as d <-> R-1-d, 0 as d <-> R-d
+        const C mine = (tid == 0) ? v[(R - s) % R] : v[R - 1 - s];
+        const int src_lane = special ? lane : (lane ^ 16);
+        C zz;
+        zz.x = __shfl_sync(0xffffffffu, mine.x, src_lane);
+        zz.y = __shfl_sync(0xffffffffu, mine.y, src_lane);
+        if (s == 0 && tid == 0) continue;  // bins 0 and NC: left over
         const int k = bj + NQ * s, mbin = NC - k;
-        if (s == 0 && tid == 0) {
-          // DC and Nyquist are real: X[0] = Re Z0 + Im Z0, X[NC] = Re Z0 - Im Z0
-          const C z0 = v[0];
-          const MagD m0 = analysis_real_bin(z0.x + z0.y, sk[0].p, sk[0].mag);
-          const MagD mn = analysis_real_bin(z0.x - z0.y, sm[0].p, sm[0].mag);
-          if (emit) {
-            scatter(dk[0], sk[0], fabsf(m0.mag), m0.d, __float_as_uint(m0.mag) >> 31, rs, rl);
-            scatter(dm[0], sm[0], fabsf(mn.mag), mn.d, __float_as_uint(mn.mag) >> 31, rs, rl);
-          }
-          continue;
-        }
-        const bool need_k = dk[s].j >= 0, need_m = dm[s].j >= 0;
-        if (!need_k && !need_m) continue;
-        const C za = v[s], zz = zc[s], w = wpair[s];
+        const C za = v[s];
+        const C w = pair_twiddle<N>(wpair0, s);
         const double er = 0.5 * (za.x + zz.x), ei = 0.5 * (za.y - zz.y);
         const double dr = 0.5 * (za.x - zz.x), di = 0.5 * (za.y + zz.y);
         const double tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
-        float mag;
-        int dq;
-        bool flip;
-        if (need_k) {
-          const C xk{er + ti_, ei - tr_};
-          analysis_bin(xk.x, xk.y, sk[s].x.x, sk[s].x.y, sk[s].p, sk[s].mag, k, false, mag, dq, flip);
-          sk[s].x = xk;
-          if (emit) {
-            scatter(dk[s], sk[s], mag, dq, flip, rs, rl);
-            if (s == 0 && k >= kmin && k <= kmax) {
-              pk_mag[gg * PKB + k - kmin] = flip ? -mag : mag;
-              pk_d[gg * PKB + k - kmin] = dq;
+        float magk, magm;
+        int dk, dm;
+        bool fk, fm;
+        const C xk{er + ti_, ei - tr_};
+        analysis_bin(xk.x, xk.y, sk[s].x.x, sk[s].x.y, sk[s].p, sk[s].mag, k, false, magk, dk, fk);
+        sk[s].x = xk;
+        const C xm{er - ti_, -ei - tr_};
+        analysis_bin(xm.x, xm.y, sm[s].x.x, sm[s].x.y, sm[s].p, sm[s].mag, mbin, false, magm, dm, fm);
+        sm[s].x = xm;
+        // both records into the slot this thread loaded v[s]'s input from (nobody else reads it)
+        *reinterpret_cast<uint4*>(zb + s * NQ) =
+            make_uint4(__float_as_uint(magk) | (fk ? 0x80000000u : 0u), (uint32_t)dk,
+                       __float_as_uint(magm) | (fm ? 0x80000000u : 0u), (uint32_t)dm);
+      }
+    }
+    __syncthreads();  // records of the batch complete
+
+    const int e_lo = bi == 0 ? 1 : 0;  // the chunk's leading halo frame emits nothing
+    uint2* const row0 = stage_t + (size_t)(f_first - wv.wb) * NBP;  // row of the batch's first frame
+
+    // ---- gather role: bin shift, exact phase increment, chunk-local running phase, coalesced stores
+    {
+      const int g_cnt = min(g_hi, we_rel - f_rel);  // frames before the wave end
+      uint2* const pst = row0 + tid;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) {
+        if (gg >= e_lo && gg < g_hi) {
+          const unsigned char* fbase = reinterpret_cast<const unsigned char*>(buf + gg * BUF);
+#pragma unroll
+          for (int q = 0; q < QB; ++q) {
+            if (goff[q] != 0xffffffffu) {
+              const uint2 rec = *reinterpret_cast<const uint2*>(fbase + goff[q]);
+              lacc[q] += shift_inc_a(gA[q], (int)rec.y, rec.x, r_fix);
+              if (gg == g_cnt - 1) totc[q] = lacc[q];
+              pst[gg * NBP + q * THREADS] = make_uint2(rec.x & 0x7fffffffu, lacc[q]);
             }
           }
         }
-        if (need_m) {
-          const C xm{er - ti_, -ei - tr_};
-          analysis_bin(xm.x, xm.y, sm[s].x.x, sm[s].x.y, sm[s].p, sm[s].mag, mbin, false, mag, dq, flip);
-          sm[s].x = xm;
-          if (emit) scatter(dm[s], sm[s], mag, dq, flip, rs, rl);
+      }
+    }
+    // ---- the Nyquist output bin j = NC: the last warp, one lane per frame, warp scan for the running phase
+    if (warp == THREADS / 32 - 1 && noff != 0xffffffffu) {
+      const int gg = lane;
+      const bool valid = gg < G && gg >= e_lo && gg < g_hi;
+      uint32_t inc = 0u, mbits = 0u;
+      if (valid) {
+        const uint2 rec = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(buf + gg * BUF) + noff);
+        inc = shift_inc_a(nA, (int)rec.y, rec.x, r_fix);
+        mbits = rec.x & 0x7fffffffu;
+      }
+      uint32_t run = inc;  // inclusive scan over the lanes (= frames, ascending)
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const uint32_t vv = __shfl_up_sync(0xffffffffu, run, o);
+        if (lane >= o) run += vv;
+      }
+      const uint32_t mine = lacc_nyq + run;
+      if (valid) row0[gg * NBP + NC] = make_uint2(mbits, mine);
+      const unsigned cm = __ballot_sync(0xffffffffu, valid && f_rel + gg < we_rel);
+      if (cm) totc_nyq = __shfl_sync(0xffffffffu, mine, 31 - __clz(cm));
+      lacc_nyq += __shfl_sync(0xffffffffu, run, 7);
+    }
+
+    // ---- the three left-over bins on the `spw` warp.  Magnitude and phase of a frame do not depend on its
+    //      predecessor, so the frames go in parallel; the phase advance takes the predecessor's values from
+    //      the lane below (or the carried state), the running phase is a subgroup scan.
+    if (warp == spw) {
+      const int sub = lane >> 3, fr = lane & 7;
+      const bool valid = sub < 3 && fr >= g_lo && fr < g_hi;
+      const bool emitf = valid && fr >= e_lo;
+      C X{1.0, 0.0};
+      float mag = 1.f;
+      uint32_t P = 0u;
+      if (valid) {
+        if (sub == 0) {  // bin NC/2 mirrors onto itself: X = conj(Z[NC/2])
+          const C zs = s_sp[2 * fr + 1];
+          X = C{zs.x, -zs.y};
+          analysis_polar(X.x, X.y, mag, P);
+        } else {         // DC and Nyquist are real: X[0] = Re Z0 + Im Z0, X[NC] = Re Z0 - Im Z0
+          const C z0 = s_sp[2 * fr];
+          X = C{sub == 1 ? z0.x + z0.y : z0.x - z0.y, 0.0};
+          mag = fabsf((float)X.x);
+          P = X.x < 0.0 ? 0x80000000u : 0u;
         }
       }
-      if (tid == 0 && dself.j >= 0) {  // bin NC/2 mirrors onto itself: X = conj(Z[NC/2])
-        const C zs = v[R / 2];
-        float mag;
-        int dq;
-        bool flip;
-        analysis_bin(zs.x, -zs.y, sself.x.x, sself.x.y, sself.p, sself.mag, NC / 2, false, mag, dq, flip);
-        sself.x = C{zs.x, -zs.y};
-        if (emit) scatter(dself, sself, mag, dq, flip, rs, rl);
+      C Xp;
+      Xp.x = __shfl_up_sync(0xffffffffu, X.x, 1, 8);
+      Xp.y = __shfl_up_sync(0xffffffffu, X.y, 1, 8);
+      uint32_t Pp = __shfl_up_sync(0xffffffffu, P, 1, 8);
+      float mp = __shfl_up_sync(0xffffffffu, mag, 1, 8);
+      if (fr == g_lo) {
+        Xp = ssp.x;
+        Pp = ssp.p;
+        mp = ssp.mag;
       }
-      if (emit && ff == wv.we - 1) put_totals(sc.totc + trow, emitted);  // phase the next wave starts from
+      int dq = 0;
+      bool flip = false;
+      if (sub == 0) {
+        analysis_advance(X.x, X.y, Xp.x, Xp.y, P, Pp, mag, mp, NC / 2, false, dq, flip);
+      } else {  // analysis_real_bin: arg X is 0 or pi, Im Z := +0, so d is 0 or +pi (stored as -2^31 with the flip flag)
+        flip = (P != Pp) && !(mag * mp <= 1e-18f);
+        dq = flip ? (int)0x80000000u : 0;
+      }
+      uint32_t run = 0u;
+      if (emitf) run = shift_inc_a(spA, dq, __float_as_uint(mag) | (flip ? 0x80000000u : 0u), r_fix);
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const uint32_t vr = __shfl_up_sync(0xffffffffu, run, o, 8);
+        if (fr >= o) run += vr;
+      }
+      const uint32_t lacc_f = sp_lacc + run;
+      if (emitf && sp_fed) {
+        row0[fr * NBP + spj] = make_uint2(__float_as_uint(mag), lacc_f);
+        if (f_rel + fr == we_rel - 1) sc.totc[trow + spj] = lacc_f;  // phase the next wave starts from
+      }
+      if (g_hi > g_lo) {  // carry = the batch's last frame
+        const int last = (lane & 24) + g_hi - 1;
+        ssp.x.x = __shfl_sync(0xffffffffu, X.x, last);
+        ssp.x.y = __shfl_sync(0xffffffffu, X.y, last);
+        ssp.p = __shfl_sync(0xffffffffu, P, last);
+        ssp.mag = __shfl_sync(0xffffffffu, mag, last);
+        sp_lacc = __shfl_sync(0xffffffffu, lacc_f, last);
+      }
     }
-    __syncthreads();  // frame buffers free for the next batch; the band records of this one complete
 
-    // ---- peak bin (lowest k on exact ties) and f0, one warp per frame
-    for (int gg = warp + (bi == 0 ? 1 : 0); gg < G; gg += THREADS / 32) {
+    // ---- peak bin (lowest k on exact ties) and f0, one warp per frame, from the records of the band
+    for (int gg = warp + e_lo; gg < G; gg += THREADS / 32) {
+      if (f_rel + gg >= b_rel || f_rel + gg >= we_rel) break;
       const long long ff = f_first + gg;
-      if (ff >= b || ff >= wv.we) break;
-      const float* pm = pk_mag + gg * PKB - kmin;
+      const uint2* recs = reinterpret_cast<const uint2*>(buf + gg * BUF);  // record of bin k < NC/2: recs[2 k]
       float best = -1.f;
       int bk = kmin;
       for (int k = kmin + lane; k <= kmax; k += 32) {
-        const float vv = fabsf(pm[k]);
+        const float vv = __uint_as_float(recs[2 * k].x & 0x7fffffffu);
         if (vv > best) { best = vv; bk = k; }
       }
 #pragma unroll
@@ -360,26 +447,38 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
       if (lane == 0) {
         if (tr.peak) tr.peak[ff] = bk;
         if (tr.f0) {
-          long long dd = (long long)pk_d[gg * PKB + bk - kmin];
-          if (__float_as_uint(pm[bk]) >> 31) dd += (dd < 0) ? 4294967296LL : -4294967296LL;
+          const uint2 rb = recs[2 * bk];
+          long long dd = (long long)(int)rb.y;
+          if (rb.x >> 31) dd += (dd < 0) ? 4294967296LL : -4294967296LL;
           tr.f0[ff] = ((float)bk + (float)dd * 9.313225746154785e-10f) * wv.fs_over_N;  // nu = k + 4 d
         }
       }
     }
-    // (the next batch writes the band records only after its first __syncthreads)
+    __syncthreads();  // the frame buffers are rewritten by the next batch
   }
 
-  put_totals(sc.tot + trow, emitted);  // all frames of the chunk: prefix of the later chunks of this wave
-  if (b <= wv.we) {
-    put_totals(sc.totc + trow, emitted);  // every frame of the chunk lies before the wave end
-  } else if (a >= wv.we) {
-    for (int j = tid; j < NB; j += THREADS) sc.totc[trow + j] = 0u;  // none does
+  // ---- chunk totals: all frames (prefix of the later chunks of this wave) and the frames before the wave end
+#pragma unroll
+  for (int q = 0; q < QB; ++q) {
+    if (goff[q] != 0xffffffffu) {
+      sc.tot[trow + tid + q * THREADS] = lacc[q];
+      sc.totc[trow + tid + q * THREADS] = totc[q];
+    }
+  }
+  if (tid == THREADS - 1 && noff != 0xffffffffu) {
+    sc.tot[trow + NC] = lacc_nyq;
+    sc.totc[trow + NC] = totc_nyq;
+  }
+  if (sp_owner && sp_fed) {
+    sc.tot[trow + spj] = sp_lacc;
+    if (b <= wv.we) sc.totc[trow + spj] = sp_lacc;   // every frame of the chunk lies before the wave end
+    else if (a >= wv.we) sc.totc[trow + spj] = 0u;    // none does (otherwise: captured at frame we - 1)
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 bool pv_analyze2_supported(int fftN) { return fftN == 1024 || fftN == 2048; }
-int pv_analyze2_band_capacity(int fftN) { return fftN / 16; }
+int pv_analyze2_band_capacity(int fftN) { return fftN / 8 - 1; }  // the band must lie below bin fftN/8
 
 template <int N>
 static cudaError_t configure2_n() {

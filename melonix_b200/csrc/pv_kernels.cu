@@ -341,8 +341,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
       // end of the wave (their running phase is what the next wave starts from)
       const int e_lo = bi == 0 ? 1 : 0;  // the chunk's leading halo frame emits nothing
       const int g_cnt = (int)min((long long)g_hi, wv.we - f_first);
-      float* ps = sc.smag + (row0 + (size_t)(f_first - wv.wb)) * NBP + tid;
-      uint32_t* pl = sc.lacc + (row0 + (size_t)(f_first - wv.wb)) * NBP + tid;
+      uint2* pst = sc.stage + (row0 + (size_t)(f_first - wv.wb)) * NBP + tid;
       const int r_fix = (int)wv.r_fix;
 #pragma unroll
       for (int gg = 0; gg < G; ++gg) {
@@ -355,8 +354,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
               const float smag = shift_one_bin_v2(zb, scq[q], r_fix, inc);
               lacc[q] += inc;
               if (gg == g_cnt - 1) totc[q] = lacc[q];
-              ps[gg * NBP + q * THREADS] = smag;
-              pl[gg * NBP + q * THREADS] = lacc[q];
+              pst[gg * NBP + q * THREADS] = make_uint2(__float_as_uint(smag), lacc[q]);
             }
           }
         }
@@ -389,8 +387,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           const float smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
           lacc[q] += inc;
           if (counted) totc[q] = lacc[q];
-          sc.smag[row + j] = smag;
-          sc.lacc[row + j] = lacc[q];
+          sc.stage[row + j] = make_uint2(__float_as_uint(smag), lacc[q]);
         }
       }
     }
@@ -426,8 +423,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         const uint32_t mine = lacc_nyq + run;
         if (valid) {
           const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
-          sc.smag[row + NC] = smag;
-          sc.lacc[row + NC] = mine;
+          sc.stage[row + NC] = make_uint2(__float_as_uint(smag), mine);
         }
         // phase at the last frame before the wave end (carried into the next wave)
         const unsigned cm = __ballot_sync(0xffffffffu, valid && ff < wv.we);
@@ -529,7 +525,10 @@ pv_scan_kernel(int nb, int nbp, int nchunks, const PvScratch sc) {
 
 // ------------------------------------------------------------------------------------------------
 // K_S
-template <int N, int G>
+// the reference's export conversion (app.cpp:1209-1212): int16(x * 32767.), double product, truncation
+__device__ __forceinline__ short pcm16(float v) { return (short)__double2int_rz((double)v * 32767.); }
+
+template <int N, int G, bool O16>
 __global__ void __launch_bounds__(PvCfg<N, G>::THREADS, MLX_KS_MINB)
 pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = PvCfg<N, G>;
@@ -547,7 +546,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
   const PvTrack tr = tracks[blockIdx.y];
-  if (tr.out == nullptr) return;
+  if (O16 ? (tr.out16 == nullptr) : (tr.out == nullptr)) return;
   const long long hop_lim = min(wv.we, tr.F);
   const long long a = wv.wb + (long long)blockIdx.x * wv.CS;
   if (a >= hop_lim) return;
@@ -593,76 +592,63 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   auto emit_hop = [&](int hrel, int i2, float2 v) {
     if (hrel >= 0 && hrel < nhop) {
       const long long o = (a + hrel) * H + 2 * i2;
-      if (o + 1 < tr.n) {
-        *reinterpret_cast<float2*>(tr.out + o) = v;
-      } else if (o < tr.n) {
-        tr.out[o] = v.x;
+      if constexpr (O16) {
+        if (o + 1 < tr.n) {
+          *reinterpret_cast<short2*>(tr.out16 + o) = make_short2(pcm16(v.x), pcm16(v.y));
+        } else if (o < tr.n) {
+          tr.out16[o] = pcm16(v.x);
+        }
+      } else {
+        if (o + 1 < tr.n) {
+          *reinterpret_cast<float2*>(tr.out + o) = v;
+        } else if (o < tr.n) {
+          tr.out[o] = v.x;
+        }
       }
     }
   };
 
   // chunks that end inside the track (all but the last one of a track) need no per-sample bounds test
   const bool interior = b * H <= tr.n;
-  float* const pout = tr.out + a * H + 2 * tid;  // column 0 of this thread in hop a
-  const float* const psm = sc.smag + row0 * NBP;
-  const uint32_t* const pla = sc.lacc + row0 * NBP;
+  float* const pout = O16 ? nullptr : tr.out + a * H + 2 * tid;  // column 0 of this thread in hop a
+  short* const pout16 = O16 ? tr.out16 + a * H + 2 * tid : nullptr;
+  const uint2* const pst = sc.stage + row0 * NBP;
 
   for (int bi = 0; bi < nbatch; ++bi) {
     const int fb = bi * G;                       // frame index relative to a
     const int nfr = min(G, nfr_total - fb);      // frames present in this batch
     float* const pob = pout + (long long)(fb - 3) * H;  // hop fb - 3: where frame fb's first quarter completes
+    short* const pob16 = pout16 + (long long)(fb - 3) * H;
 
     // ---- synthesis spectrum Y = smag e^{i theta}, folded for the N/2-point complex inverse.
     //      All global loads of a sub-batch are issued before the first use (latency hiding).
 #pragma unroll 1
     for (int g0 = 0; g0 < nfr; g0 += GS) {
-      float mk[GS][QP], mm[GS][QP], m0[GS], mn[GS];
-      uint32_t ak[GS][QP], am[GS][QP], a0[GS], an[GS];
-      if (nfr == G) {  // full batch (all but the last of a chunk): rows at compile-time offsets
-        const float* msrc0 = psm + (size_t)(fb + g0) * NBP;
-        const uint32_t* asrc0 = pla + (size_t)(fb + g0) * NBP;
-#pragma unroll
-        for (int u = 0; u < GS; ++u) {
-          const float* msrc = msrc0 + u * NBP;
-          const uint32_t* asrc = asrc0 + u * NBP;
-#pragma unroll
-          for (int q = 0; q < QP; ++q) {
-            const int k = 1 + tid + q * THREADS;
-            if (k <= NC / 2) {
-              mk[u][q] = __ldg(msrc + k);
-              mm[u][q] = __ldg(msrc + NC - k);
-              ak[u][q] = __ldg(asrc + k);
-              am[u][q] = __ldg(asrc + NC - k);
-            }
-          }
-          if (tid == 0) {
-            m0[u] = __ldg(msrc);
-            mn[u] = __ldg(msrc + NC);
-            a0[u] = __ldg(asrc);
-            an[u] = __ldg(asrc + NC);
-          }
-        }
-      } else
-#pragma unroll
-      for (int u = 0; u < GS; ++u) {
-        const int gg = min(g0 + u, nfr - 1);  // clamp: duplicates of the last frame are never used
-        const float* msrc = sc.smag + (row0 + fb + gg) * NBP;
-        const uint32_t* asrc = sc.lacc + (row0 + fb + gg) * NBP;
+      // one 8-byte record per bin: .x = shifted magnitude (float bits), .y = chunk-local phase sum
+      uint2 rk[GS][QP], rm[GS][QP], r0[GS], rn[GS];
+      auto fetch = [&](const uint2* src, int u) {
 #pragma unroll
         for (int q = 0; q < QP; ++q) {
           const int k = 1 + tid + q * THREADS;
           if (k <= NC / 2) {
-            mk[u][q] = __ldg(msrc + k);
-            mm[u][q] = __ldg(msrc + NC - k);
-            ak[u][q] = __ldg(asrc + k);
-            am[u][q] = __ldg(asrc + NC - k);
+            rk[u][q] = __ldg(src + k);
+            rm[u][q] = __ldg(src + NC - k);
           }
         }
         if (tid == 0) {
-          m0[u] = __ldg(msrc);
-          mn[u] = __ldg(msrc + NC);
-          a0[u] = __ldg(asrc);
-          an[u] = __ldg(asrc + NC);
+          r0[u] = __ldg(src);
+          rn[u] = __ldg(src + NC);
+        }
+      };
+      if (nfr == G) {  // full batch (all but the last of a chunk): rows at compile-time offsets
+        const uint2* src0 = pst + (size_t)(fb + g0) * NBP;
+#pragma unroll
+        for (int u = 0; u < GS; ++u) fetch(src0 + u * NBP, u);
+      } else {
+#pragma unroll
+        for (int u = 0; u < GS; ++u) {
+          const int gg = min(g0 + u, nfr - 1);  // clamp: duplicates of the last frame are never used
+          fetch(sc.stage + (row0 + fb + gg) * NBP, u);
         }
       }
 #pragma unroll
@@ -693,9 +679,10 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
             if (k <= NC / 2) {
               const int mbin = NC - k;
               float sk, ck, sm, cm;
-              sincos_turns(prek[q] + ak[u][q], sk, ck);
-              sincos_turns(prem[q] + am[u][q], sm, cm);
-              const float ykr = mk[u][q] * ck, yki = mk[u][q] * sk, ymr = mm[u][q] * cm, ymi = mm[u][q] * sm;
+              sincos_turns(prek[q] + rk[u][q].y, sk, ck);
+              sincos_turns(prem[q] + rm[u][q].y, sm, cm);
+              const float mkq = __uint_as_float(rk[u][q].x), mmq = __uint_as_float(rm[u][q].x);
+              const float ykr = mkq * ck, yki = mkq * sk, ymr = mmq * cm, ymi = mmq * sm;
               // A = Y_k, B = conj(Y_m): E2 = A + B, D2 = A - B, O2 = D2 * conj(W^k)
               const float er = ykr + ymr, ei = yki - ymi;
               const float dr = ykr - ymr, di = yki + ymi;
@@ -706,9 +693,9 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
           }
           if (tid == 0) {  // Im of DC / Nyquist forced to 0
             float s0, c0, sn, cn;
-            sincos_turns(pre0 + a0[u], s0, c0);
-            sincos_turns(pren + an[u], sn, cn);
-            const float y0 = m0[u] * c0, yn = mn[u] * cn;
+            sincos_turns(pre0 + r0[u].y, s0, c0);
+            sincos_turns(pren + rn[u].y, sn, cn);
+            const float y0 = __uint_as_float(r0[u].x) * c0, yn = __uint_as_float(rn[u].x) * cn;
             zb[0] = C{y0 + yn, y0 - yn};
           }
         }
@@ -759,7 +746,12 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
             p2[c] = make_float2(q3.x, q3.y);
             if (interior) {
               const int hrel = fb + gi - 3;
-              if (hrel >= 0 && hrel < nhop) *reinterpret_cast<float2*>(pob + gi * H + 2 * c * THREADS) = o;
+              if (hrel >= 0 && hrel < nhop) {
+                if constexpr (O16)
+                  *reinterpret_cast<short2*>(pob16 + gi * H + 2 * c * THREADS) = make_short2(pcm16(o.x), pcm16(o.y));
+                else
+                  *reinterpret_cast<float2*>(pob + gi * H + 2 * c * THREADS) = o;
+              }
             } else {
               emit_hop(fb + gi - 3, i2, o);
             }
@@ -794,7 +786,10 @@ static cudaError_t configure_n() {
   e = cudaFuncSetAttribute(pv_analyze_kernel<N, GA>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(pv_synth_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(pv_synth_kernel<N, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)PvCfg<N, G>::SMEM_S);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(pv_synth_kernel<N, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)PvCfg<N, G>::SMEM_S);
 }
 
@@ -863,12 +858,43 @@ cudaError_t launch_pv_scan(int fftN, int ntracks, const PvWave& wv, const PvScra
 }
 
 cudaError_t launch_pv_synth(int fftN, const PvTrack* tracks, int ntracks, const PvWave& wv,
-                            const PvTables& tb, const PvScratch& sc, cudaStream_t st) {
+                            const PvTables& tb, const PvScratch& sc, bool out16, cudaStream_t st) {
   MLX_PV_DISPATCH(fftN, {
     constexpr int G = PvG<N>::value;
     dim3 grid(wv.nchunksS, ntracks);
-    pv_synth_kernel<N, G><<<grid, PvCfg<N, G>::THREADS, PvCfg<N, G>::SMEM_S, st>>>(tracks, wv, tb, sc);
+    if (out16)
+      pv_synth_kernel<N, G, true><<<grid, PvCfg<N, G>::THREADS, PvCfg<N, G>::SMEM_S, st>>>(tracks, wv, tb, sc);
+    else
+      pv_synth_kernel<N, G, false><<<grid, PvCfg<N, G>::THREADS, PvCfg<N, G>::SMEM_S, st>>>(tracks, wv, tb, sc);
   });
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// int16 PCM -> float, 8 samples per thread (one 16-byte load, two 16-byte stores); x = s * 2^-15 exactly
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const short* __restrict__ in, float* __restrict__ out,
+                                                             long long n) {
+  const long long i8 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i8 + 8 <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(in + i8));
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      f[2 * q] = (float)(short)(w[q] & 0xffff) * 3.0517578125e-05f;
+      f[2 * q + 1] = (float)(w[q] >> 16) * 3.0517578125e-05f;
+    }
+    *reinterpret_cast<float4*>(out + i8) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(out + i8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    for (long long i = i8; i < min(i8 + 8, n); ++i) out[i] = (float)in[i] * 3.0517578125e-05f;
+  }
+}
+
+cudaError_t launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const long long threads = (n + 7) / 8;
+  pcm16_to_float_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, out, n);
   return cudaGetLastError();
 }
 

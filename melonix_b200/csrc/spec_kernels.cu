@@ -207,7 +207,16 @@ struct SpecFramesCfg {
 
 template <int N, bool RGB>
 __global__ void __launch_bounds__(256, MLX_SPEC_MINB)
-spec_frames_kernel(const SpecArgs a, const int fpc) {
+spec_frames_kernel(const SpecArgs a0, const int fpc) {
+  SpecArgs a = a0;
+  if (a.multi) {  // batched launch: this CTA row works on track blockIdx.y
+    const SpecTrackDesc d = a.multi[blockIdx.y];
+    a.x = d.x;
+    a.n = d.n;
+    a.count = d.count;
+    a.out = d.out;
+    a.rgb = d.rgb;
+  }
   using Cfg = SpecFramesCfg<N>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, JPB = Cfg::JPB, BUF = Cfg::BUF, THREADS = Cfg::THREADS;
   constexpr bool TAB = Cfg::TAB;
@@ -374,13 +383,14 @@ static cudaError_t launch_spec_frames(const SpecArgs& a, cudaStream_t st) {
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spec_frames_kernel<N, false>, Cfg::THREADS, smem);
   if (occ < 1) occ = 1;
   // frames per CTA: whole batches, at most 32 of them, and a grid that fills the resident slots evenly
-  const long long batches = (a.count + Cfg::JPB - 1) / Cfg::JPB;
+  // (batched launch: a.count is the longest track's frame count; the CTA rows of all tracks share the slots)
+  const long long batches = (a.count + Cfg::JPB - 1) / Cfg::JPB * (a.multi ? a.ntracks : 1);
   const long long slots = (long long)sms * occ;
   const long long rounds = (batches + slots * 32 - 1) / (slots * 32);
   long long nb = (batches + slots * rounds - 1) / (slots * rounds);
   if (nb < 1) nb = 1;
   const int fpc = (int)nb * Cfg::JPB;
-  const int grid = (int)((a.count + fpc - 1) / fpc);
+  const dim3 grid((unsigned)((a.count + fpc - 1) / fpc), a.multi ? (unsigned)a.ntracks : 1u);
   if (a.rgb) spec_frames_kernel<N, true><<<grid, Cfg::THREADS, smem, st>>>(a, fpc);
   else spec_frames_kernel<N, false><<<grid, Cfg::THREADS, smem, st>>>(a, fpc);
   return cudaGetLastError();

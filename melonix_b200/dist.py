@@ -216,6 +216,65 @@ def run_time_sharded_torch(engine, owns, n_total: int, fft_n: int, hop: int, rat
     return out[0] if single else out
 
 
+# ------------------------------------------------------------------------------------------------
+# The two sharding modes that need no collective at all
+
+def shard_spec_jobs(jobs, fft_n: int, n: int, world: int, rank: int):
+    """Spec STFT jobs (reference Spec::getSpec ranges (start, end), spec.cpp:18,44-66) are independent: the
+    job list is cut into contiguous blocks and each rank needs only the samples its windows
+    [end - fft_n, end) touch -- a READ-ONLY halo that is uploaded with the shard (the host has the whole
+    file; no exchange).  Returns (slice of `jobs` owned by `rank`, need_lo, need_hi, local_jobs) where
+    local_jobs are the owned jobs in the coordinates of the uploaded window wav[need_lo:need_hi]."""
+    import numpy as np
+    jobs = np.asarray(jobs, np.int64).reshape(-1, 2)
+    own = shard_tracks(jobs.shape[0], world, rank)          # same balanced contiguous split as for tracks
+    mine = jobs[own.start:own.stop]
+    if mine.shape[0] == 0:
+        return own, 0, 0, mine.astype(np.int32)
+    need_lo = int(max(0, mine[:, 1].min() - fft_n))          # indices < 0 read as zero (spec.cpp:50-54)
+    need_hi = int(min(n, max(mine[:, 1].max(), need_lo)))
+    return own, need_lo, need_hi, (mine - need_lo).astype(np.int32)
+
+
+def run_spec_sharded(engine, wav, jobs, fft_n: int, world: int, rank: int):
+    """This rank's block of Spec columns: uploads wav[need_lo:need_hi] only, returns (job slice,
+    [count, fft_n/2] float32).  Rows of different ranks concatenate to the unsharded result, bit for bit."""
+    import numpy as np
+    own, lo, hi, local = shard_spec_jobs(jobs, fft_n, len(wav), world, rank)
+    if local.shape[0] == 0:
+        return own, np.zeros((0, fft_n // 2), np.float32)
+    engine.upload_tracks([np.ascontiguousarray(wav[lo:hi], np.float32)])
+    return own, engine.spec_batch(0, fft_n, local)
+
+
+def shard_grain_rows(out_off, world: int, rank: int):
+    """Grain path (reference App::process / exportWav, app.cpp:294-345, 1194-1215): the cursor recurrence
+    that produces the render schedule is serial but O(#grains) and stays on the host; given the schedule,
+    every output sample depends only on its own row, so the rows are cut where the OUTPUT sample count
+    balances.  Returns the half-open row range [r0, r1) of `rank` (replicas of the source track, disjoint
+    outputs, no collective)."""
+    import numpy as np
+    off = np.asarray(out_off, np.int64)
+    rows = off.size - 1
+    total = int(off[-1]) if rows >= 0 else 0
+    cut = [int(np.searchsorted(off, total * r // world, side="left")) for r in range(world + 1)]
+    cut[0], cut[-1] = 0, rows
+    cut = [min(max(c, 0), rows) for c in cut]
+    return cut[rank], max(cut[rank], cut[rank + 1])
+
+
+def run_grain_sharded(engine, track: int, sched: dict, world: int, rank: int):
+    """Renders this rank's rows of an export schedule (melonix_b200.hostlib.export_schedule) with
+    mlx_grain_render: (first output sample, float32 pcm, int16 pcm).  The reference's trailing zeros
+    (app.cpp:303-309) belong to the last rank."""
+    r0, r1 = shard_grain_rows(sched["out_off"], world, rank)
+    off = sched["out_off"][r0:r1 + 1] - sched["out_off"][r0]
+    tail = sched["tail_zeros"] if rank == world - 1 else 0
+    pcm, pcm16 = engine.grain_render(track, sched["gstart"][r0:r1], sched["glen"][r0:r1], sched["rate"][r0:r1], off,
+                                     sched["next"][r0:r1], tail_zeros=tail)
+    return int(sched["out_off"][r0]), pcm, pcm16
+
+
 def bind_to_gpu_numa_node(device: int) -> dict:
     """Pins the calling process to the CPUs of the NUMA node the GPU hangs off, so that pinned host
     buffers allocated afterwards (first touch) and the copy-issuing threads are local to the GPU's

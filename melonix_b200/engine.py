@@ -116,6 +116,10 @@ class Engine:
         assert out.is_cuda and out.is_contiguous() and out.numel() >= count * (fftN // 2)
         check(self._L.mlx_spec_frames_dev(self._h, track, fftN, hop, first_frame, count, out.data_ptr()))
 
+    def spec_frames_all_dev(self, fftN: int, hop: int, outs) -> None:
+        """Every uploaded track in one launch: outs[t] = float32 CUDA tensor [F_t, fftN/2]."""
+        check(self._L.mlx_spec_frames_all_dev(self._h, fftN, hop, ptr_array([o.data_ptr() for o in outs])))
+
     # ------------------------------------------------------------------ PV path
     def _params(self, fftN, hop, rate, sample_rate, frame_begin=-1, frame_end=-1, wave_mib=0,
                 phase_in=None, rate_per_frame=None) -> PvParams:
@@ -208,7 +212,9 @@ class Engine:
 
     def pv_process_host(self, tracks, fftN: int, hop: int, rate: float, out_wav, out_peak=None,
                         out_f0=None, sample_rate: float = 48000.0, wave_mib: int = 0) -> None:
-        """End to end from host buffers (numpy arrays or pinned torch CPU tensors) into host buffers."""
+        """End to end from host buffers (numpy arrays or pinned torch CPU tensors) into host buffers.
+        float32 or int16 PCM on either side (mlx_pv_process_host_fmt): int16 in = s / 32768, int16 out =
+        int16(x * 32767.) by truncation, the reference's export conversion (app.cpp:1209-1212)."""
         def addr(a):
             if a is None:
                 return None
@@ -217,6 +223,14 @@ class Engine:
         def size(a):
             return a.size if isinstance(a, np.ndarray) else a.numel()
 
+        def fmt(seq):
+            kinds = {str(a.dtype).replace("torch.", "") for a in seq if a is not None}
+            if kinds <= {"float32"}:
+                return 0
+            if kinds == {"int16"}:
+                return 1
+            raise TypeError(f"tracks must be all float32 or all int16, got {sorted(kinds)}")
+
         p = self._params(fftN, hop, rate, sample_rate, -1, -1, wave_mib)
         nt = len(tracks)
         pin = ptr_array([addr(t) for t in tracks])
@@ -224,7 +238,8 @@ class Engine:
         pw = ptr_array([addr(t) for t in (out_wav or [None] * nt)])
         pp = ptr_array([addr(t) for t in (out_peak or [None] * nt)])
         pf = ptr_array([addr(t) for t in (out_f0 or [None] * nt)])
-        check(self._L.mlx_pv_process_host(self._h, C.byref(p), pin, ns, nt, pw, pp, pf))
+        check(self._L.mlx_pv_process_host_fmt(self._h, C.byref(p), pin, fmt(tracks), ns, nt, pw,
+                                              fmt(out_wav or []), pp, pf))
         self._lens = [size(t) for t in tracks]
 
     # ------------------------------------------------------------------ grain path

@@ -55,6 +55,52 @@ def test_c_abi_shard_rule_matches_closed_form():
                     assert (s.need_lo, s.need_hi) == (off * H, min(n, (fe + 3) * H))
 
 
+def test_spec_job_shards_cover_and_halo(oracle):
+    """shard_spec_jobs: blocks partition the job list; evaluating a rank's LOCAL jobs on its uploaded window
+    (here with the CPU oracle standing in for the kernel) gives exactly the rows of the unsharded run --
+    regular hops, the reference geometry (32768 / 375), ragged ends, more ranks than jobs."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import signals as S
+    x = S.vibrato_tone(1.5, seed=3)
+    for N, hop in ((1024, 256), (4096, 375)):
+        jobs = S.regular_jobs(x.size, hop)
+        full = oracle.spec_batch(x, N, jobs, nthreads=2)
+        for w in (1, 2, 3, 8):
+            rows = []
+            for r in range(w):
+                own, lo, hi, local = D.shard_spec_jobs(jobs, N, x.size, w, r)
+                assert 0 <= lo <= hi <= x.size and local.shape[0] == len(own)
+                if len(own):
+                    assert lo == max(0, int(jobs[own.start:own.stop, 1].min()) - N)
+                    rows.append(oracle.spec_batch(x[lo:hi], N, local, nthreads=2))
+            assert np.array_equal(np.concatenate(rows), full), (N, hop, w)
+    own, lo, hi, local = D.shard_spec_jobs(jobs[:2], 1024, x.size, 8, 5)
+    assert len(own) == 0 and local.shape[0] == 0
+
+
+def test_grain_row_shards_partition_the_output(oracle):
+    """shard_grain_rows: row ranges are contiguous, cover every row once and balance the output samples;
+    concatenating per-shard renders (CPU oracle resampler standing in for the kernel) equals the whole."""
+    from melonix_b200 import hostlib as H
+    sys.path.insert(0, str(ROOT / "tests"))
+    import signals as S
+    x = S.two_tone(6.0)
+    markers = [(10, 0, 0, 3.0), (x.size - 10, 0, 0, 3.0)]
+    gs, gl = H.grain_segment(x)
+    sch = H.export_schedule(x, 48000, markers, gs, gl)
+    rows = sch["gstart"].size
+    whole = oracle.grain_export(x, 48000, markers)["pcm"]
+    for w in (1, 2, 3, 8, rows + 5):
+        cuts = [D.shard_grain_rows(sch["out_off"], w, r) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == rows
+        assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:])) and all(a <= b for a, b in cuts)
+        sizes = [int(sch["out_off"][b] - sch["out_off"][a]) for a, b in cuts]
+        assert sum(sizes) == int(sch["out_off"][-1])
+        if w <= 8:
+            assert max(sizes) - min(sizes) <= 2 * int(np.diff(sch["out_off"]).max())
+    assert whole.size == int(sch["out_off"][-1]) + sch["tail_zeros"]
+
+
 def _worker(rank, world, port, n, N, H, out):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:

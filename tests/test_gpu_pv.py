@@ -311,6 +311,7 @@ def test_pitch_up_kernel_is_bitwise_the_general_kernel(engine, monkeypatch, N):
                     monkeypatch.setenv("MLX_PV_NO_KA2", "1")
                 else:
                     monkeypatch.delenv("MLX_PV_NO_KA2", raising=False)
+                    monkeypatch.setenv("MLX_PV_KA2", "1")
                 engine.upload_tracks(xs)
                 out = engine.pv_run(N, H, r, wave_mib=(1 if env else -1))
                 tots = [torch.zeros(N // 2 + 1, dtype=torch.int32, device="cuda") for _ in xs]
@@ -318,6 +319,7 @@ def test_pitch_up_kernel_is_bitwise_the_general_kernel(engine, monkeypatch, N):
                 torch.cuda.synchronize()
                 res.append((out, [t.cpu().numpy() for t in tots]))
             monkeypatch.delenv("MLX_PV_NO_KA2", raising=False)
+            monkeypatch.delenv("MLX_PV_KA2", raising=False)
             for k in env:
                 monkeypatch.delenv(k, raising=False)
             (a, ta), (b, tb) = res
@@ -353,3 +355,34 @@ def test_host_pipeline_equals_resident_run(engine):
     engine.pv_process_host(xs, 2048, 512, r, ys, pk, f0)
     for u, y, p, f in zip(a, ys, pk, f0):
         assert np.array_equal(u["y"], y) and np.array_equal(u["peak"], p) and np.array_equal(u["f0"], f)
+
+
+def test_int16_wire_formats_are_exact(engine):
+    """mlx_pv_process_host_fmt: int16 PCM in means x = s / 32768 (the same output, bit for bit, as handing in
+    those floats); int16 out is the reference's export conversion int16(x * 32767.) by truncation
+    (app.cpp:1209-1212) of the float output, bit for bit -- computed on the device, fused into K_S."""
+    xs = [S.vibrato_tone(3.0, seed=81), S.vibrato_tone(1.1, seed=82), S.two_tone(0.4), S.vibrato_tone(2.0, seed=83),
+          S.vibrato_tone(0.9, seed=84)]                               # five tracks: a group of four and a ragged one
+    r = ratio(3.0)
+    q = [np.round(x * 32767.0).astype(np.int16) for x in xs]
+    xf = [(s.astype(np.float32) / np.float32(32768.0)) for s in q]    # exact in float32
+    nf = [(x.size + 511) // 512 for x in xs]
+
+    def run(ins, out_dtype):
+        ys = [np.zeros(x.size, out_dtype) for x in xs]
+        pk = [np.zeros(n, np.int32) for n in nf]
+        f0 = [np.zeros(n, np.float32) for n in nf]
+        engine.pv_process_host(ins, 2048, 512, r, ys, pk, f0)
+        return ys, pk, f0
+
+    y_ff, pk_ff, f0_ff = run(xf, np.float32)
+    y_if, pk_if, f0_if = run(q, np.float32)
+    y_fi, _, _ = run(xf, np.int16)
+    y_ii, pk_ii, _ = run(q, np.int16)
+    engine.upload_tracks(xf)
+    ref = engine.pv_run(2048, 512, r)
+    for t in range(len(xs)):
+        assert np.array_equal(y_ff[t], ref[t]["y"]) and np.array_equal(pk_ff[t], ref[t]["peak"])
+        assert np.array_equal(y_if[t], y_ff[t]) and np.array_equal(pk_if[t], pk_ff[t]) and np.array_equal(f0_if[t], f0_ff[t])
+        want = np.trunc(y_ff[t].astype(np.float64) * 32767.0).astype(np.int16)
+        assert np.array_equal(y_fi[t], want) and np.array_equal(y_ii[t], want) and np.array_equal(pk_ii[t], pk_ff[t])

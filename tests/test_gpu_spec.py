@@ -156,3 +156,24 @@ def test_errors_are_reported(engine):
         engine.spec_batch(3, 1024, np.array([[0, 10]], np.int32))       # no such track
     with pytest.raises(m.MlxError):
         engine.pv_run(2048, 500, 1.0)                                   # hop != N/4
+
+
+def test_all_tracks_in_one_launch_equals_per_track_launches(engine, oracle):
+    """mlx_spec_frames_all_dev (one batched K1r launch over every uploaded track, ragged lengths) against
+    the per-track launches bit for bit, and against the oracle (reference spec.cpp:44-66 semantics)."""
+    import torch
+    xs = [S.vibrato_tone(2.0, seed=91), S.vibrato_tone(0.7, seed=92), S.sine_sweep(1.3), np.zeros(300, np.float32)]
+    engine.upload_tracks(xs)
+    engine.use_torch_stream()
+    for N, hop in ((1024, 256), (2048, 512), (512, 128), (4096, 1024), (2048, 300)):
+        Fs = [(x.size + hop - 1) // hop for x in xs]
+        outs = [torch.full((F, N // 2), -1.0, dtype=torch.float32, device="cuda") for F in Fs]
+        engine.spec_frames_all_dev(N, hop, outs)
+        torch.cuda.synchronize()
+        for t, (x, F) in enumerate(zip(xs, Fs)):
+            one = torch.full((F, N // 2), -2.0, dtype=torch.float32, device="cuda")
+            engine.spec_frames_dev(t, N, hop, 0, F, one)
+            torch.cuda.synchronize()
+            assert torch.equal(outs[t], one), (N, hop, t)
+            ref = oracle.spec_batch(x, N, S.regular_jobs(x.size, hop), nthreads=2)
+            assert np.sqrt(np.mean((outs[t].cpu().numpy().astype(np.float64) - ref) ** 2)) < 1e-7

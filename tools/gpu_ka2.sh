@@ -8,6 +8,6 @@ run() { name=$1; shift
 import json,sys; d=json.loads(sys.stdin.read()); k=d['roofline']['kernel_ms_per_step']
 print('$name', 'Mframes/s %.2f'%(d['value']/1e6), 'ms %.2f'%d['ms_per_step'], {a:round(b,2) for a,b in k.items()})"
 }
-run ka2 X=1
+run ka2 MLX_PV_KA2=1
 run general MLX_PV_NO_KA2=1
-for v in "$@"; do run $v MELONIX_B200_LIB=variants/$v.so; done
+for v in "$@"; do run $v MLX_PV_KA2=1 MELONIX_B200_LIB=variants/$v.so; done
