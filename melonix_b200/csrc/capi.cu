@@ -208,11 +208,11 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
   int rc = ensure_tables(c, fftN, true, &out->tb);
   if (rc) return rc;
   CK(c->track_desc.reserve(sizeof(PvTrack) * nt));
-  CK(c->gk.reserve(sizeof(uint32_t) * 2 * NBP));  // gather table gk[NBP] + scatter table dst[NBP]
+  CK(c->gk.reserve(sizeof(uint32_t) * NBP));
   CK(c->carry.reserve(sizeof(uint32_t) * nt * NBP));
   const size_t desc_bytes = (sizeof(PvTrack) * nt + 15) & ~size_t(15);
   mlx_ctx::Slot* slot = nullptr;
-  rc = acquire_slot(c, desc_bytes + sizeof(uint32_t) * 2 * NBP, &slot);
+  rc = acquire_slot(c, desc_bytes + sizeof(uint32_t) * NBP, &slot);
   if (rc) return rc;
   PvTrack* desc = static_cast<PvTrack*>(slot->p);
   uint32_t* gk = reinterpret_cast<uint32_t*>(static_cast<char*>(slot->p) + desc_bytes);
@@ -240,19 +240,9 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
     }
     for (int j = 0; j < NB; ++j)
       if (klo[j] <= khi[j]) gk[j] = (uint32_t)klo[j] | ((uint32_t)khi[j] << 16);
-    // the same map as a scatter (K_A2): usable when every output bin is fed by at most one input bin
-    uint32_t* dst = gk + NBP;
+    // K_A2 (opt-in) needs every output bin to be fed by at most one input bin
     bool injective = true;
     for (int j = 0; j < NB; ++j) injective = injective && (klo[j] >= khi[j]);
-    for (int k = 0; k < NBP; ++k) dst[k] = 0xffffffffu;
-    for (int k = 0; k < NB; ++k) {
-      const int j = (int)std::trunc((float)k * r);
-      if (j < 0 || j >= NB) continue;
-      int jn = NB;  // output bin of the next input bin (or the end of the spectrum)
-      if (k + 1 < NB) jn = std::min(NB, (int)std::trunc((float)(k + 1) * r));
-      const int nz = std::max(0, jn - j - 1);
-      dst[k] = (uint32_t)j | ((uint32_t)nz << 16);
-    }
     if (klo[0] != 0 || khi[0] != 0) injective = false;  // output bin 0 must be fed by input bin 0
     const int kmin = std::max(1, (int)std::ceil(50.0 * fftN / p->sample_rate));
     const int kmax = std::max(kmin, std::min(fftN / 2, (int)std::floor(2000.0 * fftN / p->sample_rate)));
@@ -261,7 +251,7 @@ int pv_prepare(mlx_ctx* c, const mlx_pv_params* p, int fftN, bool synth, float* 
                       pv_ka2_enabled();
   }
   CK(cudaMemcpyAsync(c->track_desc.p, desc, sizeof(PvTrack) * nt, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->gk.p, gk, sizeof(uint32_t) * 2 * NBP, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->gk.p, gk, sizeof(uint32_t) * NBP, cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventRecord(slot->done, c->stream));
   CK(cudaMemsetAsync(c->carry.p, 0, sizeof(uint32_t) * nt * NBP, c->stream));
   if (p->phase_in_dev) {
@@ -332,12 +322,11 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
     wv.kmin = kmin;
     wv.kmax = kmax;
     wv.gk = static_cast<const uint32_t*>(c->gk.p);
-    wv.dst = pr.scatter_ok ? wv.gk + pl.NBP : nullptr;
     wv.r_fix = (long long)((double)p->rate * 67108864.0);
     if (mode != kPvSynth) {
       c->mark(0);
-      if (wv.dst)
-        CK(launch_pv_analyze2(pl.N, tdev, nt, wv, pt, sc, c->stream));  // constant ratio >= 1: K_A2
+      if (pr.scatter_ok)
+        CK(launch_pv_analyze2(pl.N, tdev, nt, wv, pt, sc, c->stream));  // constant ratio >= 1: K_A2 (opt-in)
       else
         CK(launch_pv_analyze(pl.N, tdev, nt, wv, pt, sc, c->stream));
       c->launches += 1;

@@ -50,10 +50,6 @@ struct PvWave {
   //   gk[j] = klo | khi << 16 with K_j = [klo, khi] (klo = 1, khi = 0 when empty)
   const uint32_t* gk;
   long long r_fix;  // rate * 2^26, exact (a float has 24 significant bits)
-  // scatter form of the same map for the constant-rate pitch-up kernel K_A2 (nullptr: not eligible):
-  //   dst[k] = j | nz << 16 with j = trunc(float(k) * rate) <= fftN/2 the output bin fed by input bin k and
-  //   nz the empty output bins that follow j;  0xffffffff when j lies beyond the Nyquist bin
-  const uint32_t* dst;
 };
 
 struct PvScratch {

@@ -83,18 +83,6 @@ struct Ka2Twiddle {
   cplx<double> w[1];
 };
 
-// inc of one frame for an output bin whose source record is (mag bits with the cut-flip flag in the sign,
-// d): (A + ((d * r_fix + 2^25) >> 26) + flip term) mod 2^32, A = 16 * kh * r_fix mod 2^32 -- the value of
-// pv_shift.cuh's shift_inc (base = r_fix * kh * 2^30 + 2^25 is A * 2^26 + 2^25 mod 2^64; the flip term
-// -+r_fix * 2^32 is -+64 r_fix after the shift).  An empty K_j reads the zero record with A = (j & 3) << 30.
-__device__ __forceinline__ uint32_t shift_inc_a(uint32_t A, int d, uint32_t mb, int r_fix) {
-  long long B;
-  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(B) : "r"(d), "r"(r_fix), "l"(1LL << 25));
-  const uint32_t q = __funnelshift_r((uint32_t)B, (uint32_t)((unsigned long long)B >> 32), 26);
-  const int adj = ((int)mb >> 31) & (d < 0 ? (r_fix << 6) : -(r_fix << 6));
-  return A + q + (uint32_t)adj;
-}
-
 // running state of one analysed bin across the frames of a chunk
 struct BinState {
   cplx<double> x;   // previous frame's spectrum value (for the FP64 decision at the +-pi cut)
@@ -274,47 +262,86 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
     // ---- pair role: tail butterfly, mirrored partner by shuffle, pair split, analysis, records
     const int g_hi = min(G, b_rel - f_rel);  // frames of this batch that exist: [g_lo, g_hi)
     const int g_lo = f_first < 0 ? 1 : 0;
-#pragma unroll(kKa2Unroll)
-    for (int gg = g_lo; gg < g_hi; ++gg) {
-      C* zb = buf + gg * BUF + bj;
-      C v[R];
+    //      U frames at a time, stage by stage, so that the independent work of different frames and bins
+    //      (loads, butterflies, the sqrt / atan2 of every bin) overlaps; only the cheap phase-advance step at
+    //      the end is sequential in the frame index.
+    constexpr int U = kKa2Unroll;
+    static_assert(G % U == 0, "frames per batch must be a multiple of the bin-phase unroll");
+#pragma unroll 1
+    for (int g0 = 0; g0 < G; g0 += U) {
+      if (g0 >= g_hi) break;
+      C v[U][R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = zb[r * NQ];
-      twiddle_powers<R>(v, wtail);
-      dft_r<R, -1>(v);  // v[d] = Z[bj + 256 d]
-      if (tid == 0) {
-        s_sp[2 * gg] = v[0];
-        s_sp[2 * gg + 1] = v[R / 2];
+      for (int u = 0; u < U; ++u) {
+        const C* zb = buf + (g0 + u) * BUF + bj;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[u][r] = zb[r * NQ];
       }
 #pragma unroll
-      for (int s = 0; s < SLOTS; ++s) {
-        // slot s pairs Z[bj + 256 s] with the other lane's Z[(256 - bj) + 256 (R-1-s)]; the self-mirrored
-        // butterflies pair their own outputs: 128 as d <-> R-1-d, 0 as d <-> R-d
-        const C mine = (tid == 0) ? v[(R - s) % R] : v[R - 1 - s];
-        const int src_lane = special ? lane : (lane ^ 16);
-        C zz;
-        zz.x = __shfl_sync(0xffffffffu, mine.x, src_lane);
-        zz.y = __shfl_sync(0xffffffffu, mine.y, src_lane);
-        if (s == 0 && tid == 0) continue;  // bins 0 and NC: left over
-        const int k = bj + NQ * s, mbin = NC - k;
-        const C za = v[s];
-        const C w = pair_twiddle<N>(wpair0, s);
-        const double er = 0.5 * (za.x + zz.x), ei = 0.5 * (za.y - zz.y);
-        const double dr = 0.5 * (za.x - zz.x), di = 0.5 * (za.y + zz.y);
-        const double tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
-        float magk, magm;
-        int dk, dm;
-        bool fk, fm;
-        const C xk{er + ti_, ei - tr_};
-        analysis_bin(xk.x, xk.y, sk[s].x.x, sk[s].x.y, sk[s].p, sk[s].mag, k, false, magk, dk, fk);
-        sk[s].x = xk;
-        const C xm{er - ti_, -ei - tr_};
-        analysis_bin(xm.x, xm.y, sm[s].x.x, sm[s].x.y, sm[s].p, sm[s].mag, mbin, false, magm, dm, fm);
-        sm[s].x = xm;
-        // both records into the slot this thread loaded v[s]'s input from (nobody else reads it)
-        *reinterpret_cast<uint4*>(zb + s * NQ) =
-            make_uint4(__float_as_uint(magk) | (fk ? 0x80000000u : 0u), (uint32_t)dk,
-                       __float_as_uint(magm) | (fm ? 0x80000000u : 0u), (uint32_t)dm);
+      for (int u = 0; u < U; ++u) {
+        twiddle_powers<R>(v[u], wtail);
+        dft_r<R, -1>(v[u]);  // v[u][d] = Z[bj + 256 d] of frame g0 + u
+      }
+      if (tid == 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          s_sp[2 * (g0 + u)] = v[u][0];
+          s_sp[2 * (g0 + u) + 1] = v[u][R / 2];
+        }
+      }
+      C xk[U][SLOTS], xm[U][SLOTS];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          // slot s pairs Z[bj + 256 s] with the other lane's Z[(256 - bj) + 256 (R-1-s)]; the self-mirrored
+          // butterflies pair their own outputs: 128 as d <-> R-1-d, 0 as d <-> R-d
+          const C mine = (tid == 0) ? v[u][(R - s) % R] : v[u][R - 1 - s];
+          const int src_lane = special ? lane : (lane ^ 16);
+          C zz;
+          zz.x = __shfl_sync(0xffffffffu, mine.x, src_lane);
+          zz.y = __shfl_sync(0xffffffffu, mine.y, src_lane);
+          const C za = v[u][s];
+          const C w = pair_twiddle<N>(wpair0, s);
+          const double er = 0.5 * (za.x + zz.x), ei = 0.5 * (za.y - zz.y);
+          const double dr = 0.5 * (za.x - zz.x), di = 0.5 * (za.y + zz.y);
+          const double tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
+          xk[u][s] = C{er + ti_, ei - tr_};
+          xm[u][s] = C{er - ti_, -ei - tr_};
+        }
+      }
+      float mk[U][SLOTS], mm[U][SLOTS];
+      uint32_t pk[U][SLOTS], pm[U][SLOTS];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+          analysis_polar(xk[u][s].x, xk[u][s].y, mk[u][s], pk[u][s]);
+          analysis_polar(xm[u][s].x, xm[u][s].y, mm[u][s], pm[u][s]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gg = g0 + u;
+        if (gg >= g_lo && gg < g_hi) {
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            if (s == 0 && tid == 0) continue;  // bins 0 and NC: left over
+            const int k = bj + NQ * s, mbin = NC - k;
+            int dk, dm;
+            bool fk, fm;
+            analysis_advance(xk[u][s].x, xk[u][s].y, sk[s].x.x, sk[s].x.y, pk[u][s], sk[s].p, mk[u][s], sk[s].mag, k,
+                             false, dk, fk);
+            analysis_advance(xm[u][s].x, xm[u][s].y, sm[s].x.x, sm[s].x.y, pm[u][s], sm[s].p, mm[u][s], sm[s].mag, mbin,
+                             false, dm, fm);
+            sk[s] = BinState{xk[u][s], pk[u][s], mk[u][s]};
+            sm[s] = BinState{xm[u][s], pm[u][s], mm[u][s]};
+            // both records into the slot this thread loaded v[s]'s input from (nobody else reads it)
+            *reinterpret_cast<uint4*>(buf + gg * BUF + bj + s * NQ) =
+                make_uint4(__float_as_uint(mk[u][s]) | (fk ? 0x80000000u : 0u), (uint32_t)dk,
+                           __float_as_uint(mm[u][s]) | (fm ? 0x80000000u : 0u), (uint32_t)dm);
+          }
+        }
       }
     }
     __syncthreads();  // records of the batch complete

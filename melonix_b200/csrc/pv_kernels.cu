@@ -80,8 +80,10 @@ __device__ __noinline__ void gather_entry_slow(int j, float r, int NC, uint32_t&
 template <int NC, int BUF>
 __device__ __forceinline__ float shift_one_bin(const cplx<double>* zb, int j, uint32_t kk, uint32_t r_fix,
                                                uint32_t& inc) {
-  // fft_pad(NC) is the first extra slot of the frame buffer: the Nyquist bin needs no special case
-  auto magd = [&](int k) { return *reinterpret_cast<const MagD*>(zb + fft_pad(k)); };
+  // records of the pair (k, NC - k) share the 16-byte slot of k <= NC/2 (pv_shift.cuh: rec_offset)
+  auto magd = [&](int k) {
+    return *reinterpret_cast<const MagD*>(reinterpret_cast<const unsigned char*>(zb) + rec_offset(k, NC, true));
+  };
   const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
   const bool any = klo <= khi;  // K_j non-empty (at most one bin when rate >= 1)
   const int kh = any ? khi : 0;
@@ -104,11 +106,11 @@ __device__ __forceinline__ float shift_one_bin(const cplx<double>* zb, int j, ui
 }
 
 // one frame of one output bin whose K_j has at most one element (rate >= 1); constants: pv_shift.cuh
-__device__ __forceinline__ float shift_one_bin_v2(const cplx<double>* zb, const ShiftConst& c, int r_fix,
+__device__ __forceinline__ float shift_one_bin_v2(const cplx<double>* zb, const ShiftConstA& c, int r_fix,
                                                   uint32_t& inc) {
-  const MagD mh = *reinterpret_cast<const MagD*>(zb + c.slot);
+  const MagD mh = *reinterpret_cast<const MagD*>(reinterpret_cast<const unsigned char*>(zb) + c.off);
   const uint32_t mb = __float_as_uint(mh.mag);
-  inc = shift_inc(c.base, mh.d, mb, r_fix);
+  inc = shift_inc_a(c.A, mh.d, mb, r_fix);
   return __uint_as_float(mb & 0x7fffffffu);
 }
 
@@ -170,9 +172,10 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   double* s_win = reinterpret_cast<double*>(buf + G * BUF);       // [N] when WD
   float* tile = reinterpret_cast<float*>(s_win + (WD ? N : 0));   // [2][TILE]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + 2 * TILE);  // [2]
-  static_assert(fft_pad(NC) == BUF - 2, "the Nyquist bin's (mag, d) record uses the first extra slot");
   constexpr int ZSLOT = BUF - 1;  // (mag, d) = (0, 0): what an empty K_j reads
-  auto slot = [](int k) { return fft_pad(k); };
+  auto rec = [](const C* zb, int k) {  // (mag, d) record of input bin k (pv_shift.cuh: rec_offset)
+    return *reinterpret_cast<const MagD*>(reinterpret_cast<const unsigned char*>(zb) + rec_offset(k, NC, true));
+  };
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
@@ -241,9 +244,10 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 #if MLX_GATHER_V2
   // rate >= 1: every K_j holds at most one bin and the shift of a bin is a handful of integer ops
   const bool fast_shift = !per_frame_rate && wv.rate >= 1.0f;
-  ShiftConst scq[QB];
+  ShiftConstA scq[QB];
 #pragma unroll
-  for (int q = 0; q < QB; ++q) scq[q] = make_shift_const(tid + q * THREADS, gkq[q], (uint32_t)wv.r_fix, ZSLOT);
+  for (int q = 0; q < QB; ++q)
+    scq[q] = make_shift_const_a(tid + q * THREADS, gkq[q], (uint32_t)wv.r_fix, NC, true, 16u * ZSLOT);
   for (int gg = tid; gg < G; gg += THREADS) buf[gg * BUF + ZSLOT] = C{0.0, 0.0};  // visible after the first barrier
 #endif
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
@@ -311,10 +315,13 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           int dq;
           bool flip;
           analysis_bin(xk.x, xk.y, pk[q].x, pk[q].y, ppk[q], pmk[q], k, false, mag, dq, flip);
-          // (same thread read these two slots above: overwriting them is race-free)
-          if (emit) *reinterpret_cast<MagD*>(zb + fft_pad(k)) = MagD{flip ? -mag : mag, dq};
+          const uint32_t rk0 = __float_as_uint(mag) | (flip ? 0x80000000u : 0u), rk1 = (uint32_t)dq;
           analysis_bin(xm.x, xm.y, pm[q].x, pm[q].y, ppm[q], pmm[q], mbin, false, mag, dq, flip);
-          if (emit) *reinterpret_cast<MagD*>(zb + fft_pad(mbin)) = MagD{flip ? -mag : mag, dq};
+          // both records of the pair as ONE 16-byte store into slot k (this thread read it above: race-free;
+          // 8-byte stores at a 16-byte stride were two-way bank conflicts)
+          if (emit)
+            *reinterpret_cast<uint4*>(zb + fft_pad(k)) =
+                make_uint4(rk0, rk1, __float_as_uint(mag) | (flip ? 0x80000000u : 0u), (uint32_t)dq);
           pk[q] = xk;
           pm[q] = xm;
         }
@@ -326,10 +333,9 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         const C z0 = zb[0];
         const MagD m0 = analysis_real_bin(z0.x + z0.y, pp0, pm0);
         const MagD mn = analysis_real_bin(z0.x - z0.y, ppn, pmn);
-        if (bi != 0 || gg != 0) {
-          *reinterpret_cast<MagD*>(zb) = m0;
-          *reinterpret_cast<MagD*>(zb + fft_pad(NC)) = mn;
-        }
+        if (bi != 0 || gg != 0)  // bins 0 and NC share slot 0
+          *reinterpret_cast<uint4*>(zb) = make_uint4(__float_as_uint(m0.mag), (uint32_t)m0.d, __float_as_uint(mn.mag),
+                                                     (uint32_t)mn.d);
       }
     }
     __syncthreads();
@@ -442,7 +448,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         float best = -1.f;
         int bk = wv.kmin;
         for (int k = wv.kmin + lane; k <= wv.kmax; k += 32) {
-          const float v = fabsf(reinterpret_cast<const MagD*>(zb + slot(k))->mag);
+          const float v = fabsf(rec(zb, k).mag);
           if (v > best) { best = v; bk = k; }
         }
 #pragma unroll
@@ -454,7 +460,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         if (lane == 0) {
           if (tr.peak) tr.peak[ff] = bk;
           if (tr.f0) {
-            const MagD mb = *reinterpret_cast<const MagD*>(zb + slot(bk));
+            const MagD mb = rec(zb, bk);
             long long dd = (long long)mb.d;
             if (__float_as_uint(mb.mag) >> 31) dd += (dd < 0) ? 4294967296LL : -4294967296LL;
             tr.f0[ff] = ((float)bk + (float)dd * 9.313225746154785e-10f) * wv.fs_over_N;  // nu = k + 4 d

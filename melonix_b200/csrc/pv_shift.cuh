@@ -59,4 +59,49 @@ MLX_HD uint32_t shift_inc(unsigned long long base, int d, uint32_t mb, int r_fix
 #endif
 }
 
+// ---- the same increment with a 32-bit per-bin constant.  base = r_fix * kh * 2^30 + 2^25 is A * 2^26 + 2^25
+// (mod 2^64) with A = 16 * kh * r_fix, and the flip term -+r_fix * 2^32 is -+64 r_fix after the shift, so
+//     inc = (A + ((d * r_fix + 2^25) >> 26) + flip term) mod 2^32,   A = 16 * kh * r_fix mod 2^32
+// (arithmetic shift of the signed 64-bit product = floor, which is what bits 26..57 of the sum hold).
+// An empty K_j reads the all-zero record with A = (j & 3) << 30.
+MLX_HD uint32_t shift_inc_a(uint32_t A, int d, uint32_t mb, int r_fix) {
+#ifdef __CUDA_ARCH__
+  long long B;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(B) : "r"(d), "r"(r_fix), "l"(1LL << 25));
+  const uint32_t q = __funnelshift_r((uint32_t)B, (uint32_t)((unsigned long long)B >> 32), 26);
+#else
+  const long long B = (long long)d * (long long)r_fix + (1LL << 25);
+  const uint32_t q = (uint32_t)((unsigned long long)B >> 26);
+#endif
+  const uint32_t r64 = (uint32_t)r_fix << 6;  // (mod 2^32: r_fix reaches 2^28)
+  const uint32_t adj = (uint32_t)((int)mb >> 31) & (d < 0 ? r64 : 0u - r64);
+  return A + q + adj;
+}
+
+// ---- where the (mag, d) record of input bin k lives inside a frame buffer of the analysis kernels: the
+// pair (k, NC - k), k <= NC/2, shares ONE 16-byte slot -- record of k in its first 8 bytes, of NC - k in the
+// second -- so that the thread that analysed the pair writes both with one conflict-free 16-byte store.
+// Returned: byte offset from the frame buffer's base; `padded`: slot index goes through fft_pad().
+MLX_HD uint32_t rec_offset(int k, int NC, bool padded) {
+  const int lo = k <= NC / 2 ? k : NC - k;
+  return 16u * (uint32_t)(padded ? fft_pad(lo) : lo) + (k <= NC / 2 ? 0u : 8u);
+}
+
+struct ShiftConstA {
+  uint32_t off;  // byte offset of the source record (or of the all-zero record)
+  uint32_t A;
+};
+MLX_HD ShiftConstA make_shift_const_a(int j, uint32_t kk, uint32_t r_fix, int NC, bool padded, uint32_t zero_off) {
+  const int klo = (int)(kk & 0xffffu), khi = (int)(kk >> 16);
+  ShiftConstA c;
+  if (klo <= khi) {
+    c.off = rec_offset(khi, NC, padded);
+    c.A = ((uint32_t)khi * r_fix) << 4;
+  } else {
+    c.off = zero_off;
+    c.A = ((uint32_t)j & 3u) << 30;
+  }
+  return c;
+}
+
 }  // namespace mlx

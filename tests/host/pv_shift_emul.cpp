@@ -41,6 +41,10 @@ int main() {
       const __int128 val = (__int128)r_fix * turns + ((__int128)1 << 25);
       const uint32_t exact = (uint32_t)(unsigned long long)(val >> 26);
       if (got != exact) ++bad_exact;
+      // the 32-bit-constant form used by the kernels' fast paths, and where its record lives
+      const ShiftConstA ca = make_shift_const_a(0, (uint32_t)kh | ((uint32_t)kh << 16), r_fix, 4096, true, 16u * zslot);
+      if (shift_inc_a(ca.A, d, mb, (int)r_fix) != exact) ++bad_exact;
+      if (ca.off != 16u * (uint32_t)fft_pad(kh <= 2048 ? kh : 4096 - kh) + (kh <= 2048 ? 0u : 8u)) ++bad_exact;
       // (2) the spec's double formula: one rounding each, so they agree to one count
       const double x = (double)rate * ((double)kh / 4.0 + (double)(long long)dprime / 4294967296.0);
       const double fr = x - std::floor(x);
@@ -52,6 +56,8 @@ int main() {
     for (int j = 0; j < 64; ++j) {
       const ShiftConst c = make_shift_const(j, 1u /* klo = 1, khi = 0 */, r_fix, zslot);
       if (c.slot != (uint32_t)zslot || shift_inc(c.base, 0, 0u, (int)r_fix) != ((uint32_t)(j & 3) << 30)) ++bad_exact;
+      const ShiftConstA ca = make_shift_const_a(j, 1u, r_fix, 4096, true, 16u * zslot);
+      if (ca.off != 16u * zslot || shift_inc_a(ca.A, 0, 0u, (int)r_fix) != ((uint32_t)(j & 3) << 30)) ++bad_exact;
     }
   }
   std::printf("%lld increments: %lld differ from the exact formula, %lld differ from the spec formula by more than one count\n",
