@@ -24,8 +24,10 @@ from melonix_b200 import hostlib as H  # noqa: E402
 
 
 def gather_np(a, rank, world):
-    """variable-length gather of a numpy array to rank 0 (check path only)."""
-    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    """variable-length gather of a numpy array to rank 0 (check path only; shipped as bytes: the NCCL
+    process group does not take int16 tensors)."""
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a.reshape(-1).view(np.uint8)).cuda()
     shapes = [None] * world
     dist.all_gather_object(shapes, tuple(a.shape))
     out = []
@@ -34,10 +36,11 @@ def gather_np(a, rank, world):
             if r == 0:
                 out.append(a)
             else:
-                buf = torch.empty(shapes[r], dtype=t.dtype, device="cuda")
-                if buf.numel():
+                nbytes = int(np.prod(shapes[r])) * a.dtype.itemsize
+                buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+                if nbytes:
                     dist.recv(buf, r)
-                out.append(buf.cpu().numpy())
+                out.append(buf.cpu().numpy().view(a.dtype).reshape(shapes[r]))
         elif rank == r and t.numel():
             dist.send(t, 0)
     return out
