@@ -28,6 +28,10 @@
 #define MLX_HDC constexpr
 #endif
 
+#ifndef MLX_FFT_TREE64
+#define MLX_FFT_TREE64 0  // 1: double-precision twiddle powers by the product tree too (depth 4 instead of a chain of 14)
+#endif
+
 namespace mlx {
 
 template <typename T>
@@ -175,7 +179,7 @@ MLX_HD void twiddle_powers(cplx<T> (&v)[R], const cplx<T> w) {
     v[1] = cmul(v[1], w);
     v[2] = cmul(v[2], w2);
     v[3] = cmul(v[3], cmul(w2, w));
-  } else if constexpr (sizeof(T) == 8) {
+  } else if constexpr (sizeof(T) == 8 && !MLX_FFT_TREE64) {
     // double: linear recurrence is accurate to ~R ulp(double), far more than needed
     cplx<T> p = w;
 #pragma unroll

@@ -619,10 +619,27 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   float* const pout = O16 ? nullptr : tr.out + a * H + 2 * tid;  // column 0 of this thread in hop a
   short* const pout16 = O16 ? tr.out16 + a * H + 2 * tid : nullptr;
   const uint2* const pst = sc.stage + row0 * NBP;
+#if MLX_KS_TMA
+  // The records of a batch (nfr consecutive rows = one contiguous span of the stage) arrive by ONE TMA bulk
+  // copy that is issued while the previous batch is still in its inverse FFT / overlap-add: the ~1 us
+  // latency of the global loads was the largest single stall of this kernel (17 % of the samples).
+  uint2* s_rec = reinterpret_cast<uint2*>(smem_raw + sizeof(C) * G * BUF + (MLX_KS_WIN_SMEM ? sizeof(float) * N : 0));
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rec + G * NBP);
+  if (tid == 0) mbar_init(mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)min(G, nfr_total) * NBP * (uint32_t)sizeof(uint2);
+    mbar_expect_tx(mbar, bytes);
+    tma_load_1d(s_rec, pst, bytes, mbar);
+  }
+#endif
 
   for (int bi = 0; bi < nbatch; ++bi) {
     const int fb = bi * G;                       // frame index relative to a
     const int nfr = min(G, nfr_total - fb);      // frames present in this batch
+#if MLX_KS_TMA
+    mbar_wait(mbar, bi & 1);
+#endif
     float* const pob = pout + (long long)(fb - 3) * H;  // hop fb - 3: where frame fb's first quarter completes
     short* const pob16 = pout16 + (long long)(fb - 3) * H;
 
@@ -632,6 +649,24 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     for (int g0 = 0; g0 < nfr; g0 += GS) {
       // one 8-byte record per bin: .x = shifted magnitude (float bits), .y = chunk-local phase sum
       uint2 rk[GS][QP], rm[GS][QP], r0[GS], rn[GS];
+#if MLX_KS_TMA
+      auto fetch = [&](const uint2* src, int u) {  // shared memory: unit-stride 8-byte reads, conflict-free
+#pragma unroll
+        for (int q = 0; q < QP; ++q) {
+          const int k = 1 + tid + q * THREADS;
+          if (k <= NC / 2) {
+            rk[u][q] = src[k];
+            rm[u][q] = src[NC - k];
+          }
+        }
+        if (tid == 0) {
+          r0[u] = src[0];
+          rn[u] = src[NC];
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < GS; ++u) fetch(s_rec + min(g0 + u, nfr - 1) * NBP, u);  // (clamped rows are never used)
+#else
       auto fetch = [&](const uint2* src, int u) {
 #pragma unroll
         for (int q = 0; q < QP; ++q) {
@@ -657,6 +692,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
           fetch(sc.stage + (row0 + fb + gg) * NBP, u);
         }
       }
+#endif
 #pragma unroll
       for (int u = 0; u < GS; ++u) {
         const int gg = g0 + u;
@@ -708,6 +744,14 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
       }
     }
     __syncthreads();
+#if MLX_KS_TMA
+    if (tid == 0 && bi + 1 < nbatch) {  // every thread has taken its records out of s_rec: refill for batch bi + 1
+      const uint32_t bytes = (uint32_t)min(G, nfr_total - (fb + G)) * NBP * (uint32_t)sizeof(uint2);
+      fence_proxy_async();
+      mbar_expect_tx(mbar, bytes);
+      tma_load_1d(s_rec, pst + (size_t)(fb + G) * NBP, bytes, mbar);
+    }
+#endif
 
     // ---- inverse FFT, synthesis window (includes gain and 1/N), result in place as real pairs
     if (g < nfr) {
