@@ -139,6 +139,13 @@ MLX_API int mlx_pv_phase_totals_dev(mlx_ctx *ctx, const mlx_pv_params *p, uint32
 MLX_API int mlx_pv_analyze_dev(mlx_ctx *ctx, const mlx_pv_params *p, uint32_t *const *totals_dev,
                                int32_t *const *out_peak_dev, float *const *out_f0_dev);
 MLX_API int mlx_pv_synth_dev(mlx_ctx *ctx, const mlx_pv_params *p, float *const *out_wav_dev);
+/* Inspection of a staged analysis (after mlx_pv_analyze_dev): for frames [frame_begin, frame_begin+count)
+ * of `track`, what the synthesis will be built from -- smag_dev[count][fftN/2+1] shifted magnitudes and
+ * phase_dev[count][fftN/2+1] accumulated synthesis phases in 2^-32 turns (PV-spec A.5 / A.6: the oracle's
+ * `smag` and `acc`), relative to the first analysed frame (a carried-in phase is added only at synthesis).
+ * Used by the parity tests to compare every bin of every frame with the oracle, not only the audio. */
+MLX_API int mlx_pv_stage_export_dev(mlx_ctx *ctx, int track, int64_t frame_begin, int64_t count, float *smag_dev,
+                                    uint32_t *phase_dev);
 /* End-to-end convenience for host buffers: uploads `wav`, runs, downloads, with the copies of
  * track t+1 / t-1 overlapped with the kernels of track t on separate streams. */
 MLX_API int mlx_pv_process_host(mlx_ctx *ctx, const mlx_pv_params *p, const float *const *wav,

@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
     L.mlx_pv_phase_totals_dev.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mlx_pv_analyze_dev.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mlx_pv_synth_dev.argtypes = [vp, C.POINTER(PvParams), C.POINTER(vp)]
+    L.mlx_pv_stage_export_dev.argtypes = [vp, i32, i64, i64, vp, vp]
     L.mlx_shard_frames.argtypes = [i64, i32, i32, i32, i32, C.POINTER(TimeShardC)]
     L.mlx_comm_unique_id.argtypes = [vp]
     L.mlx_comm_create.argtypes = [C.POINTER(vp), vp, vp, i32, i32]

@@ -308,6 +308,7 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
   kmax = std::min(kmax, pl.N / 2);
   kmax = std::max(kmax, kmin);
 
+  PvWave last_wv{};
   for (int64_t wb = pl.fb; wb < pl.fe; wb += pl.wave_frames) {
     PvWave wv{};
     wv.wb = wb;
@@ -334,6 +335,7 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
     c->mark(1);
     CK(launch_pv_scan(pl.N, nt, wv, sc, c->stream));
     c->launches += 1;
+    last_wv = wv;
     if (synth && mode != kPvAnalyze) {
       c->mark(2);
       CK(launch_pv_synth(pl.N, tdev, nt, wv, pt, sc, pr.out16, c->stream));
@@ -352,6 +354,8 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
     sg.nt = nt;
     sg.CA = pl.CA;
     sg.wave_frames = pl.wave_frames;
+    sg.wv = last_wv;
+    sg.sc = sc;
   }
   if (totals_dev) {
     for (int t = 0; t < nt; ++t)
@@ -716,6 +720,20 @@ int mlx_pv_synth_dev(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav_d
   if (!out_wav_dev) return fail(MLX_ERR_INVALID, "out_wav_dev is null");
   CK(cudaSetDevice(c->device));
   return pv_execute(c, &q, pl, true, out_wav_dev, nullptr, nullptr, nullptr, kPvSynth);
+}
+
+int mlx_pv_stage_export_dev(mlx_ctx* c, int track, int64_t frame_begin, int64_t count, float* smag_dev,
+                            uint32_t* phase_dev) {
+  if (!c || !smag_dev || !phase_dev) return fail(MLX_ERR_INVALID, "null argument");
+  const mlx_ctx::Staged& sg = c->staged;
+  if (!sg.valid) return fail(MLX_ERR_STATE, "mlx_pv_stage_export_dev: no staged analysis (call mlx_pv_analyze_dev first)");
+  if (track < sg.first || track >= sg.first + sg.nt) return fail(MLX_ERR_INVALID, "track is not part of the staged analysis");
+  if (count < 0 || frame_begin < sg.fb || frame_begin + count > sg.fe)
+    return fail(MLX_ERR_INVALID, "frames outside the staged range");
+  CK(cudaSetDevice(c->device));
+  CK(launch_pv_stage_export(sg.N, track - sg.first, sg.wv, sg.sc, frame_begin, count, smag_dev, phase_dev, c->stream));
+  c->launches += count > 0;
+  return MLX_OK;
 }
 
 int mlx_pv_run(mlx_ctx* c, const mlx_pv_params* p, float* const* out_wav, int32_t* const* out_peak,

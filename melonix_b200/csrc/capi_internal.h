@@ -115,6 +115,8 @@ struct mlx_ctx {
     int N = 0, first = 0, nt = 0, CA = 0;
     float rate = 0.f;
     int64_t fb = 0, fe = 0, wave_frames = 0;
+    mlx::PvWave wv{};     // the wave and scratch the analysis ran with (mlx_pv_stage_export_dev)
+    mlx::PvScratch sc{};
   } staged;
 
   const float* track_ptr(int t) const { return static_cast<const float*>(track_buf.p) + tracks[t].offset; }

@@ -78,6 +78,10 @@ cudaError_t launch_pv_synth(int fftN, const PvTrack* tracks_dev, int ntracks, co
 // int16 PCM -> float samples x = s / 32768 (exact; what the reference's decoder hands to App, swr s16 -> flt)
 cudaError_t launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t st);
 cudaError_t pv_configure(int fftN);  // cudaFuncSetAttribute for the instantiation
+// staged analysis of one track -> per frame and bin: shifted magnitude and ABSOLUTE accumulated synthesis
+// phase (chunk prefix + chunk-local sum), frames [f0, f0 + count) of the staged wave
+cudaError_t launch_pv_stage_export(int fftN, int track, const PvWave& wv, const PvScratch& sc, long long f0,
+                                   long long count, float* smag, uint32_t* phase, cudaStream_t st);
 // K_A2 (pv_analyze2.cu): constant rate >= 1, fftN in {1024, 2048}; bit-identical to launch_pv_analyze
 bool pv_analyze2_supported(int fftN);
 int pv_analyze2_band_capacity(int fftN);  // largest kmax - kmin + 1 its peak search holds

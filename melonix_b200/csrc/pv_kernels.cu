@@ -42,8 +42,10 @@
 #ifndef MLX_GATHER_V2
 #define MLX_GATHER_V2 1  // constant-rate bin shift with frame-invariant constants (bit-identical to v1)
 #endif
-#ifndef MLX_KS_MINB
-#define MLX_KS_MINB 2      // synthesis CTAs per SM the register allocation is bounded for
+#ifndef MLX_KS_MINB3_MAXN
+#define MLX_KS_MINB3_MAXN 2048  // up to this fftN: three synthesis CTAs per SM (80 registers: no register prefetch
+                                // stage -- the records come from shared memory -- and the window through L1);
+                                // measured 5.88 -> 5.71 ms on the bench batch.  Beyond: two CTAs, window in registers.
 #endif
 #ifndef MLX_KS_PRE1
 #define MLX_KS_PRE1 0      // keep the 15 stage-1 twiddle powers of the inverse FFT in registers
@@ -179,7 +181,22 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
-  const PvTrack tr = tracks[blockIdx.y];
+  // (only the fields the analysis uses: the full descriptor would sit in local memory)
+  struct {
+    const float* x;
+    long long F;
+    int* peak;
+    float* f0;
+    const float* rate_pf;
+  } tr;
+  {
+    const PvTrack* trp = tracks + blockIdx.y;
+    tr.x = trp->x;
+    tr.F = trp->F;
+    tr.peak = trp->peak;
+    tr.f0 = trp->f0;
+    tr.rate_pf = trp->rate_pf;
+  }
   const long long lim = min(wv.we + 3, tr.F);  // analysis runs three frames past the owned window
   const long long a = wv.wb + (long long)blockIdx.x * wv.CA;
   const size_t trow = ((size_t)blockIdx.y * wv.nchunksA + blockIdx.x) * NBP;
@@ -228,10 +245,13 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   }
   uint32_t pp0 = 0u, ppn = 0u;
   float pm0 = 1.f, pmn = 1.f;
-  uint32_t lacc[QB], totc[QB];  // chunk-local phase sum; its value at the last frame < we
+  // chunk-local phase sum.  Its value at the last frame before the wave end (what the next wave starts
+  // from, `totc`) goes to memory at that frame -- or at the end when the whole chunk lies before it --
+  // instead of riding along in registers.
+  uint32_t lacc[QB];
 #pragma unroll
-  for (int q = 0; q < QB; ++q) lacc[q] = totc[q] = 0u;
-  uint32_t lacc_nyq = 0u, totc_nyq = 0u;  // bin NC, kept by every lane of the last warp
+  for (int q = 0; q < QB; ++q) lacc[q] = 0u;
+  uint32_t lacc_nyq = 0u;  // bin NC, kept by every lane of the last warp
   const bool per_frame_rate = tr.rate_pf != nullptr;
   // constant-rate path: the bin-shift table entries of this thread's bins are frame-invariant
   uint32_t gkq[QB];
@@ -346,7 +366,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
       // rows of frame gg: base pointer of the batch + compile-time offsets; g_cnt = frames before the
       // end of the wave (their running phase is what the next wave starts from)
       const int e_lo = bi == 0 ? 1 : 0;  // the chunk's leading halo frame emits nothing
-      const int g_cnt = (int)min((long long)g_hi, wv.we - f_first);
+      const int g_we = (int)min((long long)G, wv.we - 1 - f_first);  // frame we - 1 inside this batch (or none)
       uint2* pst = sc.stage + (row0 + (size_t)(f_first - wv.wb)) * NBP + tid;
       const int r_fix = (int)wv.r_fix;
 #pragma unroll
@@ -359,7 +379,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
               uint32_t inc;
               const float smag = shift_one_bin_v2(zb, scq[q], r_fix, inc);
               lacc[q] += inc;
-              if (gg == g_cnt - 1) totc[q] = lacc[q];
+              if (gg == g_we) sc.totc[trow + tid + q * THREADS] = lacc[q];
               pst[gg * NBP + q * THREADS] = make_uint2(__float_as_uint(smag), lacc[q]);
             }
           }
@@ -379,7 +399,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         r = tr.rate_pf[ff];
         r_fix = (uint32_t)((double)r * 67108864.0);
       }
-      const bool counted = ff < wv.we;
+      const bool at_we = ff == wv.we - 1;
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
         const int j = tid + q * THREADS;
@@ -392,7 +412,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           }
           const float smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
           lacc[q] += inc;
-          if (counted) totc[q] = lacc[q];
+          if (at_we) sc.totc[trow + j] = lacc[q];
           sc.stage[row + j] = make_uint2(__float_as_uint(smag), lacc[q]);
         }
       }
@@ -431,9 +451,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
           sc.stage[row + NC] = make_uint2(__float_as_uint(smag), mine);
         }
-        // phase at the last frame before the wave end (carried into the next wave)
-        const unsigned cm = __ballot_sync(0xffffffffu, valid && ff < wv.we);
-        if (cm) totc_nyq = __shfl_sync(0xffffffffu, mine, 31 - __clz(cm));
+        if (valid && ff == wv.we - 1) sc.totc[trow + NC] = mine;  // phase carried into the next wave
         lacc_nyq += __shfl_sync(0xffffffffu, run, 31);
       }
     }
@@ -476,12 +494,15 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     const int j = tid + q * THREADS;
     if (j < NC) {
       sc.tot[trow + j] = lacc[q];    // all frames of the chunk: prefix of the later chunks of this wave
-      sc.totc[trow + j] = totc[q];   // frames < we only: what the next wave starts from
+      // frames < we only: every frame of the chunk (b <= we), none (a >= we), or stored at frame we - 1
+      if (b <= wv.we) sc.totc[trow + j] = lacc[q];
+      else if (a >= wv.we) sc.totc[trow + j] = 0u;
     }
   }
   if (tid == THREADS - 1) {
     sc.tot[trow + NC] = lacc_nyq;
-    sc.totc[trow + NC] = totc_nyq;
+    if (b <= wv.we) sc.totc[trow + NC] = lacc_nyq;
+    else if (a >= wv.we) sc.totc[trow + NC] = 0u;
   }
 }
 
@@ -534,15 +555,24 @@ pv_scan_kernel(int nb, int nbp, int nchunks, const PvScratch sc) {
 // the reference's export conversion (app.cpp:1209-1212): int16(x * 32767.), double product, truncation
 __device__ __forceinline__ short pcm16(float v) { return (short)__double2int_rz((double)v * 32767.); }
 
+template <int N>
+struct KsTune {
+  static constexpr bool k3 = MLX_KS_TMA && !MLX_KS_WIN_SMEM && N <= MLX_KS_MINB3_MAXN;
+  static constexpr int MINB = k3 ? 3 : 2;      // synthesis CTAs per SM the register allocation is bounded for
+  static constexpr int GS = k3 ? 1 : 4;        // frames whose records are held in registers together
+  static constexpr bool WIN_LDG = k3;          // synthesis window through L1 (__ldg) instead of 32 registers
+};
+
 template <int N, int G, bool O16>
-__global__ void __launch_bounds__(PvCfg<N, G>::THREADS, MLX_KS_MINB)
+__global__ void __launch_bounds__(PvCfg<N, G>::THREADS, KsTune<N>::MINB)
 pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = PvCfg<N, G>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NBP = Cfg::NBP;
   constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUF, QP = Cfg::QP;
   constexpr int H2 = H / 2;
   constexpr int COLS = (H2 + THREADS - 1) / THREADS;  // overlap-add columns (float2) per thread
-  constexpr int GS = G < 4 ? G : 4;  // frames whose loads are in flight together
+  constexpr int GS = G < KsTune<N>::GS ? G : KsTune<N>::GS;  // frames whose loads are in flight together
+  constexpr bool WIN_LDG = KsTune<N>::WIN_LDG;
   using C = cplx<float>;
   using F = Fft<float, NC, +1>;
 
@@ -566,12 +596,14 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   for (int i = tid; i < N; i += THREADS) s_wsyn[i] = tb.wsyn[i];
   __syncthreads();
 #else
-  float wreg[32];
+  float wreg[WIN_LDG ? 1 : 32];
+  if constexpr (!WIN_LDG) {
 #pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    const float2 w2 = *reinterpret_cast<const float2*>(tb.wsyn + 2 * (t + m * TPF));
-    wreg[2 * m] = w2.x;
-    wreg[2 * m + 1] = w2.y;
+    for (int m = 0; m < 16; ++m) {
+      const float2 w2 = *reinterpret_cast<const float2*>(tb.wsyn + 2 * (t + m * TPF));
+      wreg[2 * m] = w2.x;
+      wreg[2 * m + 1] = w2.y;
+    }
   }
 #endif
   C wr[QP];
@@ -767,8 +799,14 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
         x[m].x *= w2.x;
         x[m].y *= w2.y;
 #else
-        x[m].x *= wreg[2 * m];
-        x[m].y *= wreg[2 * m + 1];
+        if constexpr (WIN_LDG) {
+          const float2 w2 = __ldg(reinterpret_cast<const float2*>(tb.wsyn + 2 * (t + m * TPF)));  // 8 KB table: L1
+          x[m].x *= w2.x;
+          x[m].y *= w2.y;
+        } else {
+          x[m].x *= wreg[WIN_LDG ? 0 : 2 * m];
+          x[m].y *= wreg[WIN_LDG ? 0 : 2 * m + 1];
+        }
 #endif
       }
       F::store(x, zb, t);
@@ -917,6 +955,35 @@ cudaError_t launch_pv_synth(int fftN, const PvTrack* tracks, int ntracks, const 
     else
       pv_synth_kernel<N, G, false><<<grid, PvCfg<N, G>::THREADS, PvCfg<N, G>::SMEM_S, st>>>(tracks, wv, tb, sc);
   });
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// inspection of a staged analysis (mlx_pv_stage_export_dev): what K_S will synthesise from
+__global__ void __launch_bounds__(256) pv_stage_export_kernel(int nb, int nbp, int track, const PvWave wv,
+                                                              const PvScratch sc, long long f0, long long count,
+                                                              float* __restrict__ smag, uint32_t* __restrict__ phase) {
+  const long long fr = blockIdx.y;  // frame f0 + fr
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fr >= count || j >= nb) return;
+  const long long rel = f0 + fr - wv.wb;  // row of the wave
+  const int chunk = (int)(rel / wv.CA);
+  const uint2 rec = sc.stage[((size_t)track * wv.rows + (size_t)rel) * nbp + j];
+  const uint32_t pre = sc.pre[((size_t)track * wv.nchunksA + chunk) * nbp + j];
+  smag[fr * nb + j] = __uint_as_float(rec.x);
+  phase[fr * nb + j] = pre + rec.y;
+}
+
+cudaError_t launch_pv_stage_export(int fftN, int track, const PvWave& wv, const PvScratch& sc, long long f0,
+                                   long long count, float* smag, uint32_t* phase, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  const int nb = fftN / 2 + 1;
+  for (long long done = 0; done < count; done += 32768) {  // gridDim.y limit
+    const long long c = count - done < 32768 ? count - done : 32768;
+    dim3 grid((nb + 255) / 256, (unsigned)c);
+    pv_stage_export_kernel<<<grid, 256, 0, st>>>(nb, pv_nbp(fftN), track, wv, sc, f0 + done, c, smag + done * nb,
+                                                 phase + done * nb);
+  }
   return cudaGetLastError();
 }
 

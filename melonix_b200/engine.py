@@ -188,6 +188,12 @@ class Engine:
         pf = ptr_array([t.data_ptr() if t is not None else None for t in (out_f0 or [None] * nt)])
         check(self._L.mlx_pv_analyze_dev(self._h, C.byref(p), pt, pp, pf))
 
+    def pv_stage_export_dev(self, track: int, frame_begin: int, count: int, smag, phase) -> None:
+        """After pv_analyze_dev: shifted magnitudes (float32 [count, fftN/2+1]) and accumulated synthesis
+        phases (int32 view of uint32, same shape) of `count` frames of one track, into CUDA tensors."""
+        check(self._L.mlx_pv_stage_export_dev(self._h, int(track), int(frame_begin), int(count), smag.data_ptr(),
+                                              phase.data_ptr()))
+
     def pv_synth_dev(self, fftN: int, hop: int, rate: float, out_wav, sample_rate: float = 48000.0,
                      frame_begin: int = -1, frame_end: int = -1, phase_in=None) -> None:
         """Second half (mlx_pv_synth_dev): carried-in phase + synthesis on the staged analysis."""

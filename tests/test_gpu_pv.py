@@ -386,3 +386,42 @@ def test_int16_wire_formats_are_exact(engine):
         assert np.array_equal(y_if[t], y_ff[t]) and np.array_equal(pk_if[t], pk_ff[t]) and np.array_equal(f0_if[t], f0_ff[t])
         want = np.trunc(y_ff[t].astype(np.float64) * 32767.0).astype(np.int16)
         assert np.array_equal(y_fi[t], want) and np.array_equal(y_ii[t], want) and np.array_equal(pk_ii[t], pk_ff[t])
+
+
+@pytest.mark.parametrize("N,semis", [(2048, 3.0), (2048, -4.0), (4096, 3.0), (1024, 7.0)])
+def test_every_bin_of_every_frame_against_the_oracle(engine, oracle, N, semis):
+    """Not only the audio: the staged analysis itself (mlx_pv_stage_export_dev) against the oracle's per-frame
+    debug output -- shifted magnitudes (PV-spec A.5) and accumulated synthesis phases (A.6) of EVERY bin of
+    EVERY frame.  A single cut decision on the other side of +-pi than the oracle's would move that bin's
+    phase by frac(rate) turns (8e8 counts at +3 st) for the rest of the track; what is allowed is the
+    telescoping error of the float phase (1e-7 rad = 70 counts of 2^-32 turn) plus one rounding per frame."""
+    import torch
+    H = N // 4
+    x = S.vibrato_tone(20.0, seed=1234)
+    r = ratio(semis)
+    o = oracle.pv_run(x, N, H, r, want_debug=True, want_audio=False)
+    acc = np.cumsum(o["inc"].astype(np.uint64), axis=0).astype(np.uint32)      # mod 2^32
+    F, nb = acc.shape
+    engine.use_torch_stream()
+    engine.upload_tracks([x])
+    tot = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    engine.pv_analyze_dev(N, H, r, [tot])
+    smag = torch.empty((F, nb), dtype=torch.float32, device="cuda")
+    phase = torch.empty((F, nb), dtype=torch.int32, device="cuda")
+    engine.pv_stage_export_dev(0, 0, F, smag, phase)
+    torch.cuda.synchronize()
+    sm = smag.cpu().numpy()
+    ph = phase.cpu().numpy().view(np.uint32)
+    # magnitudes: float32 from the FP64 spectrum
+    scale = np.abs(o["smag"]).max()
+    assert np.abs(sm - o["smag"]).max() <= 2e-6 * scale
+    assert np.allclose(sm, o["smag"], rtol=5e-6, atol=1e-7 * scale)
+    # phases: signed distance on the circle, in counts of 2^-32 turn
+    d = (ph - acc).astype(np.int32).astype(np.int64)
+    worst = int(np.abs(d).max())
+    assert worst < (1 << 15), f"max phase deviation {worst} counts at frame/bin {np.unravel_index(np.abs(d).argmax(), d.shape)}"
+    # ... and it does not grow along the track (first vs last quarter of the frames)
+    q = F // 4
+    assert np.abs(d[-q:]).max() < 4 * max(64, np.abs(d[:q]).max()) or np.abs(d[-q:]).max() < (1 << 13)
+    # the totals handed to the next shard are the last frame's phases
+    assert np.array_equal(tot.cpu().numpy().view(np.uint32), ph[-1])
