@@ -329,7 +329,7 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
       if (pr.scatter_ok)
         CK(launch_pv_analyze2(pl.N, tdev, nt, wv, pt, sc, c->stream));  // constant ratio >= 1: K_A2 (opt-in)
       else
-        CK(launch_pv_analyze(pl.N, tdev, nt, wv, pt, sc, c->stream));
+        CK(launch_pv_analyze(pl.N, tdev, nt, wv, pt, sc, !p->rate_per_frame_dev && p->rate >= 1.0f, c->stream));
       c->launches += 1;
     }
     c->mark(1);

@@ -68,8 +68,9 @@ int pv_threads(int fftN);
 size_t pv_analyze_smem(int fftN);
 size_t pv_synth_smem(int fftN);
 
+// constant_rate_up: no track has per-frame ratios and the ratio is >= 1 (selects the specialised instantiation)
 cudaError_t launch_pv_analyze(int fftN, const PvTrack* tracks_dev, int ntracks, const PvWave& wv,
-                              const PvTables& tb, const PvScratch& sc, cudaStream_t st);
+                              const PvTables& tb, const PvScratch& sc, bool constant_rate_up, cudaStream_t st);
 cudaError_t launch_pv_scan(int fftN, int ntracks, const PvWave& wv, const PvScratch& sc,
                            cudaStream_t st);
 // out16: write PvTrack::out16 (int16) instead of PvTrack::out (float)

@@ -164,7 +164,20 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
   const int ju = warp * 16 + (lane & 15);             // unit, 0 .. 127
   const bool special = (ju == 0);                     // butterflies 0 and 128 mirror onto themselves
   const int bj = special ? (hside ? NQ / 2 : 0) : (hside ? NQ - ju : ju);
-  const C wtail = tb.tw_d[bj];                        // exp(-2 pi i bj / NC): twiddle of tail butterfly bj
+  // exp(-2 pi i bj / NC), the twiddle of tail butterfly bj -- formed exactly as the general kernel's last FFT
+  // stage forms it (fft.cuh, MLX_FFT_DERIVE_LAST: table value of bj mod TPF, rotated by (bj / TPF) sixteenths),
+  // so that the two kernels stay bit-identical
+  C wtail = tb.tw_d[bj % TPF];
+  switch (bj / TPF) {
+    case 1: wtail = cmul_w16<-1, 1>(wtail); break;
+    case 2: wtail = cmul_w16<-1, 2>(wtail); break;
+    case 3: wtail = cmul_w16<-1, 3>(wtail); break;
+    case 4: wtail = cmul_w16<-1, 4>(wtail); break;
+    case 5: wtail = cmul_w16<-1, 5>(wtail); break;
+    case 6: wtail = cmul_w16<-1, 6>(wtail); break;
+    case 7: wtail = cmul_w16<-1, 7>(wtail); break;
+    default: break;
+  }
   const int r_fix = (int)wv.r_fix;
   // slot s: bins kS = bj + 256 s < NC/2 and NC - kS.  Thread 0 (bj = 0): its slot 0 would be the real bins
   // 0 and NC, and bin NC/2 (from Z[NC/2], its output R/2) pairs with itself: those three are the left-over
@@ -302,7 +315,8 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
           zz.x = __shfl_sync(0xffffffffu, mine.x, src_lane);
           zz.y = __shfl_sync(0xffffffffu, mine.y, src_lane);
           const C za = v[u][s];
-          const C w = pair_twiddle<N>(wpair0, s);
+          // (the general kernel takes bin 256 s of thread 0 from the table, not by rotation: same here)
+          const C w = (tid == 0 && s > 0) ? tb.twr_d[NQ * s] : pair_twiddle<N>(wpair0, s);
           const double er = 0.5 * (za.x + zz.x), ei = 0.5 * (za.y - zz.y);
           const double dr = 0.5 * (za.x - zz.x), di = 0.5 * (za.y + zz.y);
           const double tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;

@@ -33,6 +33,9 @@
 #include "tma.cuh"
 #include "pv_common.cuh"
 
+#ifndef MLX_KA_DERIVE_WPAIR
+#define MLX_KA_DERIVE_WPAIR 1  // one pair-split twiddle per thread, the others by constant rotation (4 registers)
+#endif
 #ifndef MLX_UNROLL_PAIR
 #define MLX_UNROLL_PAIR 4
 #endif
@@ -159,7 +162,9 @@ __device__ __forceinline__ void sincos_turns(uint32_t acc, float& s, float& c) {
 
 // ------------------------------------------------------------------------------------------------
 // K_A
-template <int N, int G>
+// FAST: the launch has one constant ratio >= 1 for every track (the host checks): the per-frame-rate and
+// multi-bin-gather code, and the registers it keeps alive, are compiled out.
+template <int N, int G, bool FAST>
 __global__ void __launch_bounds__(PvCfg<N, G>::THREADS, PvG<N>::ka_ctas)
 pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = PvCfg<N, G>;
@@ -181,22 +186,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
-  // (only the fields the analysis uses: the full descriptor would sit in local memory)
-  struct {
-    const float* x;
-    long long F;
-    int* peak;
-    float* f0;
-    const float* rate_pf;
-  } tr;
-  {
-    const PvTrack* trp = tracks + blockIdx.y;
-    tr.x = trp->x;
-    tr.F = trp->F;
-    tr.peak = trp->peak;
-    tr.f0 = trp->f0;
-    tr.rate_pf = trp->rate_pf;
-  }
+  const PvTrack tr = tracks[blockIdx.y];
   const long long lim = min(wv.we + 3, tr.F);  // analysis runs three frames past the owned window
   const long long a = wv.wb + (long long)blockIdx.x * wv.CA;
   const size_t trow = ((size_t)blockIdx.y * wv.nchunksA + blockIdx.x) * NBP;
@@ -245,14 +235,11 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   }
   uint32_t pp0 = 0u, ppn = 0u;
   float pm0 = 1.f, pmn = 1.f;
-  // chunk-local phase sum.  Its value at the last frame before the wave end (what the next wave starts
-  // from, `totc`) goes to memory at that frame -- or at the end when the whole chunk lies before it --
-  // instead of riding along in registers.
-  uint32_t lacc[QB];
+  uint32_t lacc[QB], totc[QB];  // chunk-local phase sum; its value at the last frame < we
 #pragma unroll
-  for (int q = 0; q < QB; ++q) lacc[q] = 0u;
-  uint32_t lacc_nyq = 0u;  // bin NC, kept by every lane of the last warp
-  const bool per_frame_rate = tr.rate_pf != nullptr;
+  for (int q = 0; q < QB; ++q) lacc[q] = totc[q] = 0u;
+  uint32_t lacc_nyq = 0u, totc_nyq = 0u;  // bin NC, kept by every lane of the last warp
+  const bool per_frame_rate = FAST ? false : (tr.rate_pf != nullptr);
   // constant-rate path: the bin-shift table entries of this thread's bins are frame-invariant
   uint32_t gkq[QB];
 #pragma unroll
@@ -263,7 +250,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   const uint32_t gk_nyq = per_frame_rate ? 1u : __ldg(wv.gk + NC);
 #if MLX_GATHER_V2
   // rate >= 1: every K_j holds at most one bin and the shift of a bin is a handful of integer ops
-  const bool fast_shift = !per_frame_rate && wv.rate >= 1.0f;
+  const bool fast_shift = FAST ? true : (!per_frame_rate && wv.rate >= 1.0f);
   ShiftConstA scq[QB];
 #pragma unroll
   for (int q = 0; q < QB; ++q)
@@ -325,7 +312,22 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           const int mbin = NC - k;
           const C za = zb[fft_pad(k)];
           const C zc = zb[fft_pad(mbin)];
+#if MLX_KA_DERIVE_WPAIR
+          // pair q's twiddle = pair 0's rotated by exp(-2 pi i q THREADS / N) = q * (16 THREADS / N) sixteenths
+          C w = wpair[0];
+          constexpr int STEP16 = 16 * THREADS / N;
+          static_assert(QP == 1 || (16 * THREADS) % N == 0, "pair twiddles are a whole number of sixteenths apart");
+          switch (q * STEP16) {
+            case 1: w = cmul_w16<-1, 1>(w); break;
+            case 2: w = cmul_w16<-1, 2>(w); break;
+            case 3: w = cmul_w16<-1, 3>(w); break;
+            case 4: w = cmul_w16<-1, 4>(w); break;
+            case 6: w = cmul_w16<-1, 6>(w); break;
+            default: break;
+          }
+#else
           const C w = wpair[q];
+#endif
           const double er = 0.5 * (za.x + zc.x), ei = 0.5 * (za.y - zc.y);
           const double dr = 0.5 * (za.x - zc.x), di = 0.5 * (za.y + zc.y);
           const double tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
@@ -366,7 +368,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
       // rows of frame gg: base pointer of the batch + compile-time offsets; g_cnt = frames before the
       // end of the wave (their running phase is what the next wave starts from)
       const int e_lo = bi == 0 ? 1 : 0;  // the chunk's leading halo frame emits nothing
-      const int g_we = (int)min((long long)G, wv.we - 1 - f_first);  // frame we - 1 inside this batch (or none)
+      const int g_cnt = (int)min((long long)g_hi, wv.we - f_first);
       uint2* pst = sc.stage + (row0 + (size_t)(f_first - wv.wb)) * NBP + tid;
       const int r_fix = (int)wv.r_fix;
 #pragma unroll
@@ -379,7 +381,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
               uint32_t inc;
               const float smag = shift_one_bin_v2(zb, scq[q], r_fix, inc);
               lacc[q] += inc;
-              if (gg == g_we) sc.totc[trow + tid + q * THREADS] = lacc[q];
+              if (gg == g_cnt - 1) totc[q] = lacc[q];
               pst[gg * NBP + q * THREADS] = make_uint2(__float_as_uint(smag), lacc[q]);
             }
           }
@@ -399,7 +401,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         r = tr.rate_pf[ff];
         r_fix = (uint32_t)((double)r * 67108864.0);
       }
-      const bool at_we = ff == wv.we - 1;
+      const bool counted = ff < wv.we;
 #pragma unroll
       for (int q = 0; q < QB; ++q) {
         const int j = tid + q * THREADS;
@@ -412,7 +414,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           }
           const float smag = shift_one_bin<NC, BUF>(zb, j, kk, r_fix, inc);
           lacc[q] += inc;
-          if (at_we) sc.totc[trow + j] = lacc[q];
+          if (counted) totc[q] = lacc[q];
           sc.stage[row + j] = make_uint2(__float_as_uint(smag), lacc[q]);
         }
       }
@@ -451,7 +453,9 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           const size_t row = (row0 + (size_t)(ff - wv.wb)) * NBP;
           sc.stage[row + NC] = make_uint2(__float_as_uint(smag), mine);
         }
-        if (valid && ff == wv.we - 1) sc.totc[trow + NC] = mine;  // phase carried into the next wave
+        // phase at the last frame before the wave end (carried into the next wave)
+        const unsigned cm = __ballot_sync(0xffffffffu, valid && ff < wv.we);
+        if (cm) totc_nyq = __shfl_sync(0xffffffffu, mine, 31 - __clz(cm));
         lacc_nyq += __shfl_sync(0xffffffffu, run, 31);
       }
     }
@@ -494,15 +498,12 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     const int j = tid + q * THREADS;
     if (j < NC) {
       sc.tot[trow + j] = lacc[q];    // all frames of the chunk: prefix of the later chunks of this wave
-      // frames < we only: every frame of the chunk (b <= we), none (a >= we), or stored at frame we - 1
-      if (b <= wv.we) sc.totc[trow + j] = lacc[q];
-      else if (a >= wv.we) sc.totc[trow + j] = 0u;
+      sc.totc[trow + j] = totc[q];   // frames < we only: what the next wave starts from
     }
   }
   if (tid == THREADS - 1) {
     sc.tot[trow + NC] = lacc_nyq;
-    if (b <= wv.we) sc.totc[trow + NC] = lacc_nyq;
-    else if (a >= wv.we) sc.totc[trow + NC] = 0u;
+    sc.totc[trow + NC] = totc_nyq;
   }
 }
 
@@ -866,14 +867,15 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
 template <int N>
 static cudaError_t configure_n() {
   constexpr int G = PvG<N>::value, GA = PvG<N>::analyze;
-  cudaError_t e = cudaFuncSetAttribute(pv_analyze_kernel<N, GA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)PvCfg<N, GA>::SMEM_A);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
   // the analysis kernel lives on shared memory: ask for the largest carve-out so that MLX_KA_CTAS
   // CTAs are resident
-  e = cudaFuncSetAttribute(pv_analyze_kernel<N, GA>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           (int)cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
+  for (const void* fn : {(const void*)pv_analyze_kernel<N, GA, false>, (const void*)pv_analyze_kernel<N, GA, true>}) {
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PvCfg<N, GA>::SMEM_A);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
   e = cudaFuncSetAttribute(pv_synth_kernel<N, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)PvCfg<N, G>::SMEM_S);
   if (e != cudaSuccess) return e;
@@ -929,11 +931,14 @@ size_t pv_synth_smem(int fftN) {
 }
 
 cudaError_t launch_pv_analyze(int fftN, const PvTrack* tracks, int ntracks, const PvWave& wv,
-                              const PvTables& tb, const PvScratch& sc, cudaStream_t st) {
+                              const PvTables& tb, const PvScratch& sc, bool constant_rate_up, cudaStream_t st) {
   MLX_PV_DISPATCH(fftN, {
     constexpr int G = PvG<N>::analyze;
     dim3 grid(wv.nchunksA, ntracks);
-    pv_analyze_kernel<N, G><<<grid, PvCfg<N, G>::THREADS, PvCfg<N, G>::SMEM_A, st>>>(tracks, wv, tb, sc);
+    if (constant_rate_up)
+      pv_analyze_kernel<N, G, true><<<grid, PvCfg<N, G>::THREADS, PvCfg<N, G>::SMEM_A, st>>>(tracks, wv, tb, sc);
+    else
+      pv_analyze_kernel<N, G, false><<<grid, PvCfg<N, G>::THREADS, PvCfg<N, G>::SMEM_A, st>>>(tracks, wv, tb, sc);
   });
   return cudaGetLastError();
 }
