@@ -113,6 +113,30 @@ MLX_HD cplx<T> cmul_w16(const cplx<T> a) {
   }
 }
 
+// The same rotation with the order of operations pinned (one rounded product, one fused multiply-add per
+// component): used where a twiddle is DERIVED from another one in two different kernels that must agree bit
+// for bit -- left to the compiler, which of the two products gets fused may differ between inlined copies.
+template <int DIR, int M16>
+MLX_HD cplx<double> rot16_pinned(const cplx<double> a) {
+  constexpr int m = ((M16 % 16) + 16) % 16;
+  if constexpr (m % 4 == 0) {
+    return cmul_w16<DIR, M16>(a);  // exact: no rounding at all
+  } else {
+    constexpr double h = 0.70710678118654752440084436210485;
+    constexpr double c1 = 0.92387953251128675612818318939679, s1 = 0.38268343236508977172845998403040;
+    constexpr double c = (m % 2 == 0) ? ((m == 2 || m == 14) ? h : -h)
+                                      : ((m == 1 || m == 15) ? c1 : (m == 3 || m == 13) ? s1 : (m == 5 || m == 11) ? -s1 : -c1);
+    constexpr double s0 = (m % 2 == 0) ? ((m == 2 || m == 6) ? h : -h)
+                                       : ((m == 1 || m == 7) ? s1 : (m == 3 || m == 5) ? c1 : (m == 9 || m == 15) ? -s1 : -c1);
+    constexpr double s = DIR > 0 ? s0 : -s0;
+#ifdef __CUDA_ARCH__
+    return cplx<double>{fma(a.x, c, -__dmul_rn(a.y, s)), fma(a.x, s, __dmul_rn(a.y, c))};
+#else
+    return cplx<double>{a.x * c - a.y * s, a.x * s + a.y * c};
+#endif
+  }
+}
+
 template <int DIR, typename T>
 MLX_HD void dft8(cplx<T> (&v)[8]) {
   // n = 2a + b, k = c + 4d
@@ -319,13 +343,13 @@ struct Fft {
         const C w0 = tw.w[P::woff(S)];
         C wb = w0;
         switch (b) {
-          case 1: wb = cmul_w16<DIR, 1>(w0); break;
-          case 2: wb = cmul_w16<DIR, 2>(w0); break;
-          case 3: wb = cmul_w16<DIR, 3>(w0); break;
-          case 4: wb = cmul_w16<DIR, 4>(w0); break;
-          case 5: wb = cmul_w16<DIR, 5>(w0); break;
-          case 6: wb = cmul_w16<DIR, 6>(w0); break;
-          case 7: wb = cmul_w16<DIR, 7>(w0); break;
+          case 1: wb = rot16_pinned<DIR, 1>(w0); break;
+          case 2: wb = rot16_pinned<DIR, 2>(w0); break;
+          case 3: wb = rot16_pinned<DIR, 3>(w0); break;
+          case 4: wb = rot16_pinned<DIR, 4>(w0); break;
+          case 5: wb = rot16_pinned<DIR, 5>(w0); break;
+          case 6: wb = rot16_pinned<DIR, 6>(w0); break;
+          case 7: wb = rot16_pinned<DIR, 7>(w0); break;
           default: break;
         }
         twiddle_powers<R>(v, wb);

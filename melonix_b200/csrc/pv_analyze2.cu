@@ -101,9 +101,9 @@ __device__ __forceinline__ cplx<double> pair_twiddle(const cplx<double> w0, int 
   // cmul_w16<-1, M>: multiply by exp(-2 pi i M / 16); 256 s / N turns = (4096 s / N) sixteenths
   constexpr int STEP = 4096 / N;  // N = 2048 -> 2, N = 4096 -> 1 (N = 1024 has one slot)
   switch (s * STEP) {
-    case 1: return cmul_w16<-1, 1>(w0);
-    case 2: return cmul_w16<-1, 2>(w0);
-    case 3: return cmul_w16<-1, 3>(w0);
+    case 1: return rot16_pinned<-1, 1>(w0);
+    case 2: return rot16_pinned<-1, 2>(w0);
+    case 3: return rot16_pinned<-1, 3>(w0);
     default: return w0;
   }
 }
@@ -169,13 +169,13 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
   // so that the two kernels stay bit-identical
   C wtail = tb.tw_d[bj % TPF];
   switch (bj / TPF) {
-    case 1: wtail = cmul_w16<-1, 1>(wtail); break;
-    case 2: wtail = cmul_w16<-1, 2>(wtail); break;
-    case 3: wtail = cmul_w16<-1, 3>(wtail); break;
-    case 4: wtail = cmul_w16<-1, 4>(wtail); break;
-    case 5: wtail = cmul_w16<-1, 5>(wtail); break;
-    case 6: wtail = cmul_w16<-1, 6>(wtail); break;
-    case 7: wtail = cmul_w16<-1, 7>(wtail); break;
+    case 1: wtail = rot16_pinned<-1, 1>(wtail); break;
+    case 2: wtail = rot16_pinned<-1, 2>(wtail); break;
+    case 3: wtail = rot16_pinned<-1, 3>(wtail); break;
+    case 4: wtail = rot16_pinned<-1, 4>(wtail); break;
+    case 5: wtail = rot16_pinned<-1, 5>(wtail); break;
+    case 6: wtail = rot16_pinned<-1, 6>(wtail); break;
+    case 7: wtail = rot16_pinned<-1, 7>(wtail); break;
     default: break;
   }
   const int r_fix = (int)wv.r_fix;
@@ -200,6 +200,22 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
   const uint32_t spA = ((uint32_t)spk * (uint32_t)r_fix) << 4;
   BinState ssp{C{1.0, 0.0}, 0u, 1.f};
   uint32_t sp_lacc = 0u;
+  // exp(-2 pi i (NC/2) / N) as the general kernel forms it for its pair k = NC/2 (thread (k-1) % T, pair (k-1) / T
+  // of its T threads: table value rotated by (k-1)/T * 16 T / N sixteenths; pv_kernels.cu, MLX_KA_DERIVE_WPAIR)
+  C wself;
+  {
+    constexpr int T1 = PvCfg<N, PvG<N>::analyze>::THREADS;
+    constexpr int q = (NC / 2 - 1) / T1;
+    wself = tb.twr_d[NC / 2 - q * T1];
+    switch (q * (16 * T1 / N)) {
+      case 1: wself = rot16_pinned<-1, 1>(wself); break;
+      case 2: wself = rot16_pinned<-1, 2>(wself); break;
+      case 3: wself = rot16_pinned<-1, 3>(wself); break;
+      case 4: wself = rot16_pinned<-1, 4>(wself); break;
+      case 6: wself = rot16_pinned<-1, 6>(wself); break;
+      default: break;
+    }
+  }
 
   // ---- gather role: output bins j = tid + 256 q (and bin NC: the last warp, one lane per frame)
   //   goff: byte offset of the source record inside a frame buffer (0xffffffff: fed by a left-over bin,
@@ -417,9 +433,13 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
       float mag = 1.f;
       uint32_t P = 0u;
       if (valid) {
-        if (sub == 0) {  // bin NC/2 mirrors onto itself: X = conj(Z[NC/2])
+        if (sub == 0) {  // bin NC/2 mirrors onto itself: X = conj(Z[NC/2]) -- through the pair-split formula
+                         // with za = zc and the general kernel's (rotated) twiddle, to stay bit-identical to it
           const C zs = s_sp[2 * fr + 1];
-          X = C{zs.x, -zs.y};
+          const double di = 0.5 * (zs.y + zs.y), er = 0.5 * (zs.x + zs.x), ei = 0.5 * (zs.y - zs.y);
+          const double dr = 0.5 * (zs.x - zs.x);
+          const double tr_ = dr * wself.x - di * wself.y, ti_ = dr * wself.y + di * wself.x;
+          X = C{er + ti_, ei - tr_};
           analysis_polar(X.x, X.y, mag, P);
         } else {         // DC and Nyquist are real: X[0] = Re Z0 + Im Z0, X[NC] = Re Z0 - Im Z0
           const C z0 = s_sp[2 * fr];
