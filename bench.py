@@ -594,7 +594,7 @@ def main():
                         h2d_bytes_per_step=int(nt * n * bps), d2h_bytes_per_step=int(nt * n * bps + nt * F * 8),
                         ms_per_step=1e3 * el / steps, steps=steps, sample_format=f"{fmt} in, {fmt} out",
                         api="mlx_pv_process_host_fmt (C ABI; pinned host buffers; H2D / D2H on copy streams overlapped "
-                            "with the kernels, tracks in groups of 4 per launch)")
+                            "with the kernels, tracks in groups of 2 per launch)")
 
         e2e_f32 = run_e2e(torch.float32, max(1, min(2, args.e2e_steps)))
         e2e = run_e2e(torch.int16, args.e2e_steps)

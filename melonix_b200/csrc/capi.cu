@@ -833,8 +833,11 @@ static int pv_process_host_impl(mlx_ctx* c, const mlx_pv_params* p, const void* 
   rc = pv_prepare(c, p, p->fftN, true, out16 ? nullptr : dw.data(), dp.data(), df.data(), &pr,
                   out16 ? dw16.data() : nullptr);
   if (rc) return rc;
-  // tracks per launch group
-  int grp = 4;
+  // tracks per launch group.  Measured on the bench batch with int16 on the wire (tools/e2e_probe.py: the
+  // pure-copy floor of the same bytes is 40.5 ms): 1 / 2 / 4 / 8 / 16 tracks per group -> 43.4 / 43.9 / 45.2 /
+  // 47.3 / 53.0 ms.  Small groups win -- the kernels stay hidden under the copies either way and the drain
+  // after the last upload is shorter; 2 keeps some margin for the kernels (222 CTAs per launch).
+  int grp = 2;
   if (const char* e = getenv("MLX_PV_HOST_GROUP")) grp = std::max(1, atoi(e));
   grp = std::min(grp, ntracks);
   // scratch for the largest group, allocated before the pipeline starts (no cudaMalloc between launches)
