@@ -4,7 +4,7 @@
 # tools/summarise_profiles.py r2 turns it into profiles/.
 mkdir -p gpurun_out
 o=gpurun_out
-( time python -m pytest tests -m gpu -x -q ) > $o/final_pytest.log 2>&1; tail -4 $o/final_pytest.log
+( time python -m pytest tests -m gpu -x -q -rs ) > $o/final_pytest.log 2>&1; tail -4 $o/final_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > $o/final_smoke.log 2>&1; tail -2 $o/final_smoke.log
 python bench.py --impl reference > $o/final_bench_ref.json 2> $o/final_bench_ref.err
 python bench.py > $o/final_bench_n1.json 2> $o/final_bench_n1.err; tail -c 400 $o/final_bench_n1.json

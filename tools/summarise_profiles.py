@@ -17,7 +17,7 @@ prof = ROOT / "profiles"
 # ---- bench lines and secondary sweeps
 for a, b in (("final_bench_n1.json", f"{tag}_bench_n1.json"), ("final_bench_ref.json", f"{tag}_bench_reference_arm.json"),
              ("final_extra.json", f"{tag}_extra.json"), ("final_seg_probe.log", f"{tag}_grain_segment_probe.txt"), ("final_picks_probe.log", f"{tag}_picks_probe.txt"), ("final_grain_probe.log", f"{tag}_grain_render_probe.txt"),
-             ("bench_n2.json", f"{tag}_bench_n2.json"), ("cfg4_n2.json", f"{tag}_cfg4_sharded_n2.json")):
+             ("final_pytest.log", f"{tag}_pytest_gpu.log"), ("final_smoke.log", f"{tag}_smoke.log")):
     if (src / a).exists():
         txt = (src / a).read_text()
         if a.endswith(".json") and not txt.lstrip().startswith("{"):  # multi-rank runs: keep the JSON line only
