@@ -36,10 +36,6 @@
 #ifndef MLX_KA_DERIVE_WPAIR
 #define MLX_KA_DERIVE_WPAIR 1  // one pair-split twiddle per thread, the others by constant rotation (4 registers)
 #endif
-#ifndef MLX_KA_RELOAD
-#define MLX_KA_RELOAD 0  // FAST instantiation: bin-shift constants and the pair twiddle are re-read from their (L1-resident)
-                         // tables once per batch instead of being kept in 12 registers across the FFT phase (experiment)
-#endif
 #ifndef MLX_KA_TOTC_DIRECT
 #define MLX_KA_TOTC_DIRECT 1  // FAST instantiation: the phase at the wave end goes to memory at frame we - 1 instead of
                               // riding along in QB registers (196 -> 96 bytes of spills; 13.8 -> 13.2 ms)
@@ -68,18 +64,6 @@ constexpr int kUnrollGather = MLX_UNROLL_GATHER;  // frames of the gather phase 
 
 // ------------------------------------------------------------------------------------------------
 // scalar helpers shared by K_A / K_S
-
-// loads the compiler may not hoist out of the batch loop (their point is NOT to live in registers across the FFT phase)
-__device__ __forceinline__ uint32_t ld_nc_once_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ cplx<double> ld_nc_once_c64(const cplx<double>* p) {
-  cplx<double> v;
-  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-}
 
 // trunc(float(k) * r) with a plain float multiply, exactly as the spec (A.5) and the oracle do.
 __device__ __forceinline__ int shift_bin(int k, float r) { return (int)truncf(__fmul_rn((float)k, r)); }
@@ -319,8 +303,6 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     // phi = 0 <=> X = 1, the initial value of "previous".
     const int g_hi = (int)min((long long)G, b - f_first);
     const int g_lo = f_first < 0 ? 1 : 0;
-    C wpair_b = C{1.0, 0.0};
-    if (MLX_KA_RELOAD && FAST) wpair_b = ld_nc_once_c64(tb.twr_d + (1 + tid <= NC / 2 ? 1 + tid : 0));
 #pragma unroll(kUnrollPair)
     for (int gg = 0; gg < G; ++gg) {
       if (gg >= g_hi) break;
@@ -336,7 +318,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           const C zc = zb[fft_pad(mbin)];
 #if MLX_KA_DERIVE_WPAIR
           // pair q's twiddle = pair 0's rotated by exp(-2 pi i q THREADS / N) = q * (16 THREADS / N) sixteenths
-          C w = (MLX_KA_RELOAD && FAST) ? wpair_b : wpair[0];
+          C w = wpair[0];
           constexpr int STEP16 = 16 * THREADS / N;
           static_assert(QP == 1 || (16 * THREADS) % N == 0, "pair twiddles are a whole number of sixteenths apart");
           switch (q * STEP16) {
@@ -396,16 +378,6 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 #endif
       uint2* pst = sc.stage + (row0 + (size_t)(f_first - wv.wb)) * NBP + tid;
       const int r_fix = (int)wv.r_fix;
-      ShiftConstA scb[QB];
-#pragma unroll
-      for (int q = 0; q < QB; ++q) {
-        if (MLX_KA_RELOAD && FAST) {
-          const int j = tid + q * THREADS;
-          scb[q] = make_shift_const_a(j, j < NC ? ld_nc_once_u32(wv.gk + j) : 1u, (uint32_t)r_fix, NC, true, 16u * ZSLOT);
-        } else {
-          scb[q] = scq[q];
-        }
-      }
 #pragma unroll
       for (int gg = 0; gg < G; ++gg) {
         if (gg >= e_lo && gg < g_hi) {
@@ -414,7 +386,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
           for (int q = 0; q < QB; ++q) {
             if (tid + q * THREADS < NC) {
               uint32_t inc;
-              const float smag = shift_one_bin_v2(zb, scb[q], r_fix, inc);
+              const float smag = shift_one_bin_v2(zb, scq[q], r_fix, inc);
               lacc[q] += inc;
 #if MLX_KA_TOTC_DIRECT
               if (FAST) {
