@@ -33,6 +33,11 @@
                                // uses it rotated by the constant exp(DIR 2 pi i b / 16) (4 operations) instead of
                                // 16/R twiddle registers (K_A: 12 registers, 176 -> 88 bytes of spills, 14.05 -> 13.5 ms)
 #endif
+#ifndef MLX_FFT_PACKED_F32
+#define MLX_FFT_PACKED_F32 1  // single-precision complex add / subtract as ONE packed FADD2 (sm_100a): K1r 1.106 -> 1.037 ms at
+                              // 1024/256, K_S 5.71 -> 5.65 ms; FFMA2 runs at half the scalar issue rate (tools/ubench/fp32x2_probe.cu),
+                              // so only the issue slots are saved, not pipe cycles
+#endif
 #ifndef MLX_FFT_TREE64
 #define MLX_FFT_TREE64 0  // 1: double-precision twiddle powers by the product tree too (depth 4 instead of a chain of 14)
 #endif
@@ -56,6 +61,20 @@ template <typename T>
 MLX_HD cplx<T> csub(const cplx<T> a, const cplx<T> b) {
   return cplx<T>{a.x - b.x, a.y - b.y};
 }
+#if defined(__CUDA_ARCH__) && MLX_FFT_PACKED_F32
+// sm_100a packed single precision: a complex float is one aligned 64-bit register pair, so a complex
+// add / subtract is ONE FADD2 (the negation folds into the operand modifier).  Same rounding as two FADDs.
+template <>
+MLX_HD cplx<float> cadd<float>(const cplx<float> a, const cplx<float> b) {
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return cplx<float>{r.x, r.y};
+}
+template <>
+MLX_HD cplx<float> csub<float>(const cplx<float> a, const cplx<float> b) {
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+  return cplx<float>{r.x, r.y};
+}
+#endif
 // multiply by DIR*i  (DIR = -1: forward transform, e^{-i...};  DIR = +1: inverse)
 template <int DIR, typename T>
 MLX_HD cplx<T> cmul_i(const cplx<T> a) {

@@ -425,3 +425,32 @@ def test_every_bin_of_every_frame_against_the_oracle(engine, oracle, N, semis):
     assert np.abs(d[-q:]).max() < 4 * max(64, np.abs(d[:q]).max()) or np.abs(d[-q:]).max() < (1 << 13)
     # the totals handed to the next shard are the last frame's phases
     assert np.array_equal(tot.cpu().numpy().view(np.uint32), ph[-1])
+
+
+@pytest.mark.parametrize("N", [1024, 2048, 4096])
+def test_parseval_on_the_analysis_magnitudes(engine, N):
+    """Energy conservation of K_A's spectrum, checked with numpy alone (no code shared with the oracle or with
+    tests/np_pv_reference.py): at rate 1 the bin shift is the identity, so the staged magnitudes are |X_k| of
+    the Hann-windowed frame and  sum_n (w x)^2 = (|X_0|^2 + |X_{N/2}|^2 + 2 sum_{0<k<N/2} |X_k|^2) / N
+    must hold for every frame (float32 magnitudes: 1e-5 relative)."""
+    import torch
+    H = N // 4
+    x = S.vibrato_tone(6.0, seed=77)
+    engine.use_torch_stream()
+    engine.upload_tracks([x])
+    F = (x.size + H - 1) // H
+    nb = N // 2 + 1
+    tot = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    engine.pv_analyze_dev(N, H, 1.0, [tot])
+    smag = torch.empty((F, nb), dtype=torch.float32, device="cuda")
+    phase = torch.empty((F, nb), dtype=torch.int32, device="cuda")
+    engine.pv_stage_export_dev(0, 0, F, smag, phase)
+    torch.cuda.synchronize()
+    m2 = smag.cpu().numpy().astype(np.float64) ** 2
+    spec_energy = (m2[:, 0] + m2[:, -1] + 2.0 * m2[:, 1:-1].sum(axis=1)) / N
+    # frame f covers samples [(f+1)H - N, (f+1)H), zero outside the track (spec.cpp:47-54 convention)
+    xp = np.concatenate([np.zeros(N, np.float64), x.astype(np.float64), np.zeros(N, np.float64)])
+    w = (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(N) / N)).astype(np.float32).astype(np.float64)
+    idx = (np.arange(F)[:, None] + 1) * H + np.arange(N)[None, :]       # + N (front padding) - N (frame start)
+    time_energy = ((xp[idx] * w[None, :]) ** 2).sum(axis=1)
+    assert np.allclose(spec_energy, time_energy, rtol=1e-5, atol=1e-9)
