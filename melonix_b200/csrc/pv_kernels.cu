@@ -209,8 +209,11 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     mbar_init(mbar + 1, 1);
   }
   if constexpr (WD) {
-    for (int i = tid; i < N; i += THREADS) s_win[i] = tb.win_d[i];
+    // staged at HALF scale: the pair split X = E + W O works on Z / 2 and needs no halving of its own (a power
+    // of two: every product and sum of the transform scales exactly, the results are bit-identical)
+    for (int i = tid; i < N; i += THREADS) s_win[i] = 0.5 * tb.win_d[i];
   }
+  constexpr double kSplit = WD ? 1.0 : 0.5;  // what the pair split still has to apply
   __syncthreads();  // mbarriers initialised, window staged
   if (tid == 0) {   // first tile: samples [(a-1-3)H, (a-1+G)H) of the zero-padded track
     mbar_expect_tx(mbar, TILE * sizeof(float));
@@ -332,8 +335,8 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 #else
           const C w = wpair[q];
 #endif
-          const double er = 0.5 * (za.x + zc.x), ei = 0.5 * (za.y - zc.y);
-          const double dr = 0.5 * (za.x - zc.x), di = 0.5 * (za.y + zc.y);
+          const double er = kSplit * (za.x + zc.x), ei = kSplit * (za.y - zc.y);
+          const double dr = kSplit * (za.x - zc.x), di = kSplit * (za.y + zc.y);
           const double tr_ = dr * w.x - di * w.y, ti_ = dr * w.y + di * w.x;
           const C xk{er + ti_, ei - tr_};
           const C xm{er - ti_, -ei - tr_};
@@ -357,8 +360,9 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
       for (int gg = g_lo; gg < g_hi; ++gg) {
         C* zb = buf + gg * BUF;
         const C z0 = zb[0];
-        const MagD m0 = analysis_real_bin(z0.x + z0.y, pp0, pm0);
-        const MagD mn = analysis_real_bin(z0.x - z0.y, ppn, pmn);
+        constexpr double kReal = WD ? 2.0 : 1.0;  // Z is staged at half scale when the window is
+        const MagD m0 = analysis_real_bin(kReal * (z0.x + z0.y), pp0, pm0);
+        const MagD mn = analysis_real_bin(kReal * (z0.x - z0.y), ppn, pmn);
         if (bi != 0 || gg != 0)  // bins 0 and NC share slot 0
           *reinterpret_cast<uint4*>(zb) = make_uint4(__float_as_uint(m0.mag), (uint32_t)m0.d, __float_as_uint(mn.mag),
                                                      (uint32_t)mn.d);
@@ -459,9 +463,9 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
             smag = shift_one_bin<NC, BUF>(buf + gg * BUF, NC, kk, r_fix, inc);
           }
         }
-        uint32_t run = inc;  // inclusive scan over the lanes (= frames, ascending)
+        uint32_t run = inc;  // inclusive scan over the lanes (= frames, ascending); lanes >= G hold 0
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int o = 1; o < (G < 32 ? G : 32); o <<= 1) {
           const uint32_t v = __shfl_up_sync(0xffffffffu, run, o);
           if (lane >= o) run += v;
         }
@@ -473,7 +477,7 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         // phase at the last frame before the wave end (carried into the next wave)
         const unsigned cm = __ballot_sync(0xffffffffu, valid && ff < wv.we);
         if (cm) totc_nyq = __shfl_sync(0xffffffffu, mine, 31 - __clz(cm));
-        lacc_nyq += __shfl_sync(0xffffffffu, run, 31);
+        lacc_nyq += __shfl_sync(0xffffffffu, run, (G < 32 ? G : 32) - 1);  // the batch total (lanes >= G hold 0)
       }
     }
 
@@ -484,18 +488,19 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
         const long long ff = f_first + gg;
         if (ff >= b || ff >= wv.we) break;
         const C* zb = buf + gg * BUF;
-        float best = -1.f;
+        // Non-negative floats order like their bit patterns, so the maximum over the warp is ONE integer
+        // warp reduction and "lowest k on exact ties" a second one (10 shuffles + compares before: the four
+        // warps doing this keep the other four waiting at the barrier below).  fmaxf(., 0) maps a NaN
+        // magnitude to 0, which is what `v > best` did with it.
+        uint32_t bb = 0u;
         int bk = wv.kmin;
+#pragma unroll 4
         for (int k = wv.kmin + lane; k <= wv.kmax; k += 32) {
-          const float v = fabsf(rec(zb, k).mag);
-          if (v > best) { best = v; bk = k; }
+          const uint32_t v = __float_as_uint(fmaxf(fabsf(rec(zb, k).mag), 0.f));
+          if (v > bb) { bb = v; bk = k; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-          const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-          if (ov > best || (ov == best && ok < bk)) { best = ov; bk = ok; }
-        }
+        const uint32_t best = __reduce_max_sync(0xffffffffu, bb);
+        bk = (int)__reduce_min_sync(0xffffffffu, bb == best ? (uint32_t)bk : 0x7fffffffu);
         if (lane == 0) {
           if (tr.peak) tr.peak[ff] = bk;
           if (tr.f0) {

@@ -82,6 +82,9 @@ MLX_HD uint32_t shift_inc_a(uint32_t A, int d, uint32_t mb, int r_fix) {
 // pair (k, NC - k), k <= NC/2, shares ONE 16-byte slot -- record of k in its first 8 bytes, of NC - k in the
 // second -- so that the thread that analysed the pair writes both with one conflict-free 16-byte store.
 // Returned: byte offset from the frame buffer's base; `padded`: slot index goes through fft_pad().
+// (Alternating the halves with bit 3 of the slot index, plus one all-zero record per pair of banks, removes
+// part of the two-way conflicts of the gather phase's 8-byte reads -- measured: 60 M fewer wavefronts of
+// 2 500 M per step and no change in the kernel time, so the plain layout stays.)
 MLX_HD uint32_t rec_offset(int k, int NC, bool padded) {
   const int lo = k <= NC / 2 ? k : NC - k;
   return 16u * (uint32_t)(padded ? fft_pad(lo) : lo) + (k <= NC / 2 ? 0u : 8u);

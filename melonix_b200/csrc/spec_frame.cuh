@@ -48,10 +48,15 @@ struct SpecFrame {
 
   // After the FFT x[m] = Z[t + m*TPF].  Bin k = t + q*TPF (q < 8) pairs with bin NC - k, which is
   // slot 15 - q (16 - q for t = 0) of thread (TPF - t) mod TPF: only the upper slots are exchanged.
+  // They are staged UNPADDED, slot m at (m - 8)*TPF + t: Z[NC - k] is then element (8 - q)*TPF - t, so the
+  // lanes of a warp read consecutive 8-byte words in descending order -- one wavefront per half-warp (in the
+  // padded transform layout the descending run crosses a padding element: two-way conflicts, 16 of the 284
+  // shared-memory wavefronts of a 1024-point frame).  The staging area overlaps other threads' transform
+  // slots: the caller synchronises the group between the last stage's loads and stage_upper().
   static MLX_HD void stage_upper(const C (&x)[16], C* buf, int t) {
-    C* p = buf + fft_pad(t);
+    C* p = buf + t;
 #pragma unroll
-    for (int m = 8; m < 16; ++m) p[m * F::SLOT_STRIDE] = x[m];
+    for (int m = 8; m < 16; ++m) p[(m - 8) * TPF] = x[m];
   }
 
   // |X[k]| / N for the bins of this thread: X[k] = E[k] + W^k O[k] from Z[k] and Z[NC-k]; the split
@@ -63,7 +68,7 @@ struct SpecFrame {
     for (int q = 0; q < 8; ++q) {
       const int k = t + q * TPF;
       const C za = x[q];
-      C zc = buf[fft_pad((NC - k) & (NC - 1))];
+      C zc = buf[(8 - q) * TPF - t];  // q == 0, t == 0 reads one element past the staging area (inside the buffer)
       if (q == 0 && t == 0) zc = za;  // Z[NC] == Z[0] (slot 0 is not staged)
       const C w = twr(k);             // exp(-2 pi i k / N)
       const float er = za.x + zc.x, ei = za.y - zc.y;

@@ -292,6 +292,7 @@ spec_frames_kernel(const SpecArgs a0, const int fpc) {
     }
     if (!active) continue;
     F::run(x, buf, t, twd, bar);
+    bar.sync();  // every thread of the group has loaded its last-stage inputs: the staging area may be overwritten
     SF::stage_upper(x, buf, t);
     bar.sync();
     const long long frame = f_begin + fr;
