@@ -550,6 +550,8 @@ def main():
     roofline = dict(bound="hbm", achieved=achieved, peak=peak_gbs, unit="GB/s",
                     frac=(achieved / peak_gbs) if achieved else None,
                     traffic=(traffic or {}).get("path_bytes_per_step"),
+                    # what actually binds the FFT kernels: the L1 / shared-memory data pipe (same ncu capture)
+                    l1_data_pipe_pct_of_peak=(traffic or {}).get("l1_data_pipe_pct_of_peak"),
                     peak_source=peak_src,
                     kernel="pv_analyze + pv_scan + pv_synth (the path is three launches per wave)",
                     algorithmic_bytes_per_frame=ALGO_BYTES_PER_FRAME, frames_per_step=frames_per_rank,

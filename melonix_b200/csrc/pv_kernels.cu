@@ -591,6 +591,13 @@ struct KsTune {
   static constexpr int GS = k3 ? 1 : 4;        // frames whose records are held in registers together
   static constexpr bool WIN_LDG = k3;          // synthesis window through L1 (__ldg) instead of 32 registers
 };
+#ifndef MLX_KS_WIN_OLA
+#define MLX_KS_WIN_OLA 1  // the synthesis window is applied by the overlap-add threads: a thread owns the same output
+                          // columns for every frame, so its 8 window factors per column live in registers for the whole
+                          // kernel and the product fuses into the overlap-add (FFMA).  Applied after the inverse FFT it
+                          // cost one 8-byte L1 load per two samples and frame: 65 of the ~760 wavefronts per frame of a
+                          // kernel that runs at 87 % of the L1 / shared-memory data pipe.
+#endif
 
 template <int N, int G, bool O16>
 __global__ void __launch_bounds__(PvCfg<N, G>::THREADS, KsTune<N>::MINB)
@@ -625,8 +632,8 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   for (int i = tid; i < N; i += THREADS) s_wsyn[i] = tb.wsyn[i];
   __syncthreads();
 #else
-  float wreg[WIN_LDG ? 1 : 32];
-  if constexpr (!WIN_LDG) {
+  float wreg[(WIN_LDG || MLX_KS_WIN_OLA) ? 1 : 32];
+  if constexpr (!WIN_LDG && !MLX_KS_WIN_OLA) {
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       const float2 w2 = *reinterpret_cast<const float2*>(tb.wsyn + 2 * (t + m * TPF));
@@ -655,6 +662,16 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   float2 p0[COLS], p1[COLS], p2[COLS];  // pending overlap-add sums of the three youngest hops
 #pragma unroll
   for (int c = 0; c < COLS; ++c) p0[c] = p1[c] = p2[c] = make_float2(0.f, 0.f);
+#if MLX_KS_WIN_OLA
+  float2 wq[COLS][4];  // synthesis window (gain and 1/N included) at this thread's columns, quarter q of the frame
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    const int i2 = tid + c * THREADS;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      wq[c][q] = i2 < H2 ? __ldg(reinterpret_cast<const float2*>(tb.wsyn + q * H + 2 * i2)) : make_float2(0.f, 0.f);
+  }
+#endif
   // hop `hrel` (relative to a) of column i2: written only if this chunk owns it
   auto emit_hop = [&](int hrel, int i2, float2 v) {
     if (hrel >= 0 && hrel < nhop) {
@@ -822,7 +839,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
       bar.sync();
       F::run(x, zb, t, twd, bar);
 #pragma unroll
-      for (int m = 0; m < 16; ++m) {
+      for (int m = 0; m < (MLX_KS_WIN_OLA ? 0 : 16); ++m) {
 #if MLX_KS_WIN_SMEM
         const float2 w2 = *reinterpret_cast<const float2*>(s_wsyn + 2 * (t + m * TPF));
         x[m].x *= w2.x;
@@ -857,10 +874,17 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
             const C* yb = buf + gi * BUF;
             const C q0 = yb[fft_pad(i2)], q1 = yb[fft_pad(H2 + i2)];
             const C q2 = yb[fft_pad(2 * H2 + i2)], q3 = yb[fft_pad(3 * H2 + i2)];
+#if MLX_KS_WIN_OLA
+            const float2 o = make_float2(fmaf(q0.x, wq[c][0].x, p0[c].x), fmaf(q0.y, wq[c][0].y, p0[c].y));
+            p0[c] = make_float2(fmaf(q1.x, wq[c][1].x, p1[c].x), fmaf(q1.y, wq[c][1].y, p1[c].y));
+            p1[c] = make_float2(fmaf(q2.x, wq[c][2].x, p2[c].x), fmaf(q2.y, wq[c][2].y, p2[c].y));
+            p2[c] = make_float2(q3.x * wq[c][3].x, q3.y * wq[c][3].y);
+#else
             const float2 o = make_float2(p0[c].x + q0.x, p0[c].y + q0.y);
             p0[c] = make_float2(p1[c].x + q1.x, p1[c].y + q1.y);
             p1[c] = make_float2(p2[c].x + q2.x, p2[c].y + q2.y);
             p2[c] = make_float2(q3.x, q3.y);
+#endif
             if (interior) {
               const int hrel = fb + gi - 3;
               if (hrel >= 0 && hrel < nhop) {

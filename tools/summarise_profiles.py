@@ -49,10 +49,15 @@ keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        # the L1 / shared-memory data pipe: ONE 128-byte wavefront per cycle and SM -- the resource that binds
+        # the FFT kernels (K_S 87 %, K1r 82 %, K_A 72 % of its peak), not DRAM and not the issue slots
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "lts__t_sector_hit_rate.pct"]
 cols, table, units_of = [], {}, {}
 traffic = {}
+l1pipe = {}
 for cap in ("pv", "spec", "seg", "picks"):
     p = src / f"final_prof_{cap}.raw.csv"
     if not p.exists():
@@ -80,6 +85,9 @@ for cap in ("pv", "spec", "seg", "picks"):
         if cap == "pv":
             key = "pv_analyze" if "analyze" in name else "pv_scan" if "scan" in name else "pv_synth"
             traffic[key] = nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum")
+            k1 = "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"
+            if k1 in h:
+                l1pipe[key] = float(r[h.index(k1)])
 with open(prof / f"{tag}_ncu_full_summary.csv", "w", newline="") as f:
     w = csv.writer(f)
     w.writerow(["metric", "unit"] + cols)
@@ -88,5 +96,6 @@ with open(prof / f"{tag}_ncu_full_summary.csv", "w", newline="") as f:
 json.dump(dict(source=f"ncu --set full --clock-control none, bench.py default workload (64 tracks x 300 s, 2048/512), "
                       f"one launch each; profiles/{tag}_ncu_full_summary.csv",
                per_kernel_bytes_per_launch=traffic, path_bytes_per_step=sum(traffic.values()),
+               l1_data_pipe_pct_of_peak=l1pipe,
                algorithmic_bytes_per_step=4104 * 1800000), open(prof / "roofline_traffic.json", "w"), indent=1)
 print(json.dumps(traffic))
