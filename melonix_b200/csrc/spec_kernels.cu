@@ -247,7 +247,7 @@ spec_frames_kernel(const SpecArgs a0, const int fpc) {
     mbar_init(mbar + 1, 1);
   }
   const int ndec = N - hop;  // samples of the frame that lie before `start`
-  if constexpr (TAB) {
+  if constexpr (TAB && !MLX_SPEC_DERIVE) {
     for (int p = tid; p < N; p += THREADS) s_win[p] = p < ndec ? a.decay[ndec - p] : 1.f;
     for (int k = tid; k <= NC / 2; k += THREADS) s_twr[k] = a.twr_f[k];
   }
@@ -268,6 +268,13 @@ spec_frames_kernel(const SpecArgs a0, const int fpc) {
   if constexpr (TPF < 32) mask = ((1u << TPF) - 1u) << (((tid & 31) / TPF) * TPF);
   const SpecBar<TPF> bar{1 + g, mask};
   const float scale = 0.5f / (float)N;  // the pair split below works on 2 X
+#if MLX_SPEC_DERIVE
+  // the two exact window factors and the one split twiddle everything else of this thread is derived from
+  const float wc0 = 2 * t < ndec ? __ldg(a.decay + (ndec - 2 * t)) : 1.f;
+  const float wc1 = 2 * t + 1 < ndec ? __ldg(a.decay + (ndec - 2 * t - 1)) : 1.f;
+  const float2 w0v = __ldg(reinterpret_cast<const float2*>(a.twr_f + t));
+  const C w0{w0v.x, w0v.y};
+#endif
 
   for (int b = 0; b < nbatch; ++b) {
     const int fr = b * JPB + g;
@@ -276,6 +283,11 @@ spec_frames_kernel(const SpecArgs a0, const int fpc) {
     C x[16];
     if (active) {
       const float* cur = tile + (b & 1) * span + g * hop;
+#if MLX_SPEC_DERIVE
+      if constexpr (true) {
+        SF::load_derived(x, cur, t, wc0, wc1);
+      } else
+#endif
       if constexpr (TAB) {
         SF::load(x, cur, t, [&](int p) { return *reinterpret_cast<const C*>(s_win + p); });
       } else {
@@ -306,10 +318,15 @@ spec_frames_kernel(const SpecArgs a0, const int fpc) {
         return C{wv.x, wv.y};
       }
     };
-    SF::emit_bins(x, buf, t, scale, twr, [&](int k, float v) {
+    auto emit = [&](int k, float v) {
       if (out) out[k] = v;
       if constexpr (RGB) colour_ramp(v, a.kcol, rgb + 3 * k);
-    });
+    };
+#if MLX_SPEC_DERIVE
+    SF::template emit_bins<true>(x, buf, t, scale, twr, emit, w0);
+#else
+    SF::emit_bins(x, buf, t, scale, twr, emit);
+#endif
   }
 }
 
