@@ -32,6 +32,7 @@
 #include "pv_shift.cuh"
 #include "tma.cuh"
 #include "pv_common.cuh"
+#include "spec_frame.cuh"  // spec_rot32 / spec_mul_here: twiddles derived by compile-time rotations
 
 #ifndef MLX_KA_DERIVE_WPAIR
 #define MLX_KA_DERIVE_WPAIR 1  // one pair-split twiddle per thread, the others by constant rotation (4 registers)
@@ -591,6 +592,15 @@ struct KsTune {
   static constexpr int GS = k3 ? 1 : 4;        // frames whose records are held in registers together
   static constexpr bool WIN_LDG = k3;          // synthesis window through L1 (__ldg) instead of 32 registers
 };
+#ifndef MLX_KS_FOLD_LOCAL
+#define MLX_KS_FOLD_LOCAL 1  // the synthesis spectrum of a frame is folded by the threads that transform it: thread t
+                             // builds its own slots k = t + m*TPF (m < 8) in registers and hands the mirrored bins
+                             // NC - k -- slot 15 - m of thread TPF - t -- over through an unpadded staging area.
+                             // Before, the pair threads wrote all of Z to shared memory (8-byte stores at k = 1 + tid:
+                             // every half-warp crosses a padding element, two-way conflicts) and the transform
+                             // loaded it back: 162 wavefronts per frame against 65 now, plus 32 for the phase
+                             // prefixes that no longer fit registers (L1 loads).  Needs MLX_KS_TMA.
+#endif
 #ifndef MLX_KS_WIN_OLA
 #define MLX_KS_WIN_OLA 1  // the synthesis window is applied by the overlap-add threads: a thread owns the same output
                           // columns for every frame, so its 8 window factors per column live in registers for the whole
@@ -652,6 +662,10 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   }
   uint32_t pre0 = 0u, pren = 0u;
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
+#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
+  const float2 wf0v = __ldg(reinterpret_cast<const float2*>(tb.twr_f + t));  // exp(-2 pi i t / N)
+  const C wf0{wf0v.x, wf0v.y};
+#endif
 
   const int nbatch = (int)((flim - a + G - 1) / G);
   const int nfr_total = (int)(flim - a);
@@ -721,6 +735,64 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     float* const pob = pout + (long long)(fb - 3) * H;  // hop fb - 3: where frame fb's first quarter completes
     short* const pob16 = pout16 + (long long)(fb - 3) * H;
 
+#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
+    // ---- synthesis spectrum Y = smag e^{i theta} of frame fb + g, folded for the N/2-point complex inverse by
+    //      the group that transforms it.  Pair (k, NC - k), k = t + m*TPF: Z[k] is slot m of this thread,
+    //      Z[NC - k] slot 15 - m of thread TPF - t (slot 16 - m of thread 0 for t = 0): staged at
+    //      (8 - m)*TPF - t, where its owner reads (slot - 8)*TPF + t.  Thread 0's pair m = 0 is DC / Nyquist (one
+    //      real pair -> Z[0]); it also folds the self-paired bin NC/2 (its slot 8, staged at 0).
+    C x[16];
+    if (g < nfr) {
+      const int ca = (a_off + fb + g) / wv.CA;  // analysis chunk of this frame: its phase prefix row (L1-resident)
+      const uint32_t* pp = sc.pre + ((size_t)blockIdx.y * wv.nchunksA + ca) * NBP;
+      const uint2* src = s_rec + g * NBP;
+      C* zb = buf + g * BUF;
+      constexpr SpecRot32 rot = spec_rot32();
+      auto fold = [&](uint2 rk, uint2 rm, uint32_t pk, uint32_t pm, C w, C& zk, C& zm) {
+        float sk, ck, sm, cm;
+        sincos_turns(pk + rk.y, sk, ck);
+        sincos_turns(pm + rm.y, sm, cm);
+        const float mkq = __uint_as_float(rk.x), mmq = __uint_as_float(rm.x);
+        const float ykr = mkq * ck, yki = mkq * sk, ymr = mmq * cm, ymi = mmq * sm;
+        // A = Y_k, B = conj(Y_m): E2 = A + B, D2 = A - B, O2 = D2 * conj(W^k)
+        const float er = ykr + ymr, ei = yki - ymi;
+        const float dr = ykr - ymr, di = yki + ymi;
+        const float orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
+        zk = C{er - oi, ei + orr};
+        zm = C{er + oi, orr - ei};
+      };
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int k = t + m * TPF, mbin = NC - k;
+        const uint2 rk = src[k], rm = src[mbin];
+        const uint32_t pk = __ldg(pp + k), pm = __ldg(pp + mbin);
+        // exp(-2 pi i k / N) = w0 * exp(-2 pi i m / 32): one rotation per pair instead of eight registers (the
+        // products are pinned inside the loop: hoisted they would be fourteen registers again)
+        C w = wf0;
+        if (m != 0)
+          w = C{fmaf(-wf0.y, rot.s[m], spec_mul_here(wf0.x, rot.c[m])), fmaf(wf0.y, rot.c[m], spec_mul_here(wf0.x, rot.s[m]))};
+        C zk, zm;
+        fold(rk, rm, pk, pm, w, zk, zm);
+        int idx = (8 - m) * TPF - t;
+        if (m == 0 && t == 0) {
+          // DC / Nyquist: Im forced to 0 (the fold above ran on the pair (0, NC) and is discarded)
+          float s0, c0, sn, cn;
+          sincos_turns(pk + rk.y, s0, c0);
+          sincos_turns(pm + rm.y, sn, cn);
+          const float y0 = __uint_as_float(rk.x) * c0, yn = __uint_as_float(rm.x) * cn;
+          zk = C{y0 + yn, y0 - yn};
+          const uint2 rh = src[NC / 2];
+          const uint32_t ph = __ldg(pp + NC / 2);
+          const float2 wh = __ldg(reinterpret_cast<const float2*>(tb.twr_f + NC / 2));
+          C zdummy;
+          fold(rh, rh, ph, ph, C{wh.x, wh.y}, zm, zdummy);  // bin NC/2 pairs with itself
+          idx = 0;
+        }
+        x[m] = zk;
+        zb[idx] = zm;
+      }
+    }
+#else
     // ---- synthesis spectrum Y = smag e^{i theta}, folded for the N/2-point complex inverse.
     //      All global loads of a sub-batch are issued before the first use (latency hiding).
 #pragma unroll 1
@@ -821,6 +893,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
         }
       }
     }
+#endif
     __syncthreads();
 #if MLX_KS_TMA
     if (tid == 0 && bi + 1 < nbatch) {  // every thread has taken its records out of s_rec: refill for batch bi + 1
@@ -833,10 +906,15 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
 
     // ---- inverse FFT, synthesis window (includes gain and 1/N), result in place as real pairs
     if (g < nfr) {
-      C x[16];
       C* zb = buf + g * BUF;
+#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
+#pragma unroll
+      for (int m = 8; m < 16; ++m) x[m] = zb[(m - 8) * TPF + t];  // the mirrored bins, staged by the partner thread
+#else
+      C x[16];
       F::load(x, zb, t);
-      bar.sync();
+#endif
+      bar.sync();  // every thread of the group holds its inputs: the first stage may overwrite the buffer
       F::run(x, zb, t, twd, bar);
 #pragma unroll
       for (int m = 0; m < (MLX_KS_WIN_OLA ? 0 : 16); ++m) {
