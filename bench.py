@@ -590,11 +590,30 @@ def main():
                 estep()
             barrier()
             el = max_over_ranks(time.perf_counter() - t0)
+            # pure-copy floor of the same bytes on this box (H2D and D2H at once, no kernels): what the host <->
+            # device path alone allows, measured in the same run because it differs from box to box
+            d_in = torch.empty((nt, n), dtype=dtype, device=dev)
+            d_out = torch.empty((nt, n), dtype=dtype, device=dev)
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            floor = None
+            for _ in range(2):
+                torch.cuda.synchronize()
+                barrier()
+                t1 = time.perf_counter()
+                with torch.cuda.stream(s1):
+                    d_in.copy_(hx, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    hy.copy_(d_out, non_blocking=True)
+                torch.cuda.synchronize()
+                barrier()
+                floor = max_over_ranks(time.perf_counter() - t1)
+            del d_in, d_out
             bps = hx.element_size()
             fmt = "int16 PCM" if dtype == torch.int16 else "float32"
             return dict(value=world * frames_per_rank * steps / el, unit="frames/s",
                         h2d_bytes_per_step=int(nt * n * bps), d2h_bytes_per_step=int(nt * n * bps + nt * F * 8),
                         ms_per_step=1e3 * el / steps, steps=steps, sample_format=f"{fmt} in, {fmt} out",
+                        copy_floor_ms=1e3 * floor,
                         api="mlx_pv_process_host_fmt (C ABI; pinned host buffers; H2D / D2H on copy streams overlapped "
                             "with the kernels, tracks in groups of 2 per launch)")
 
