@@ -726,6 +726,10 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   }
 #endif
 
+#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
+  const uint32_t* const pre_trk = sc.pre + (size_t)blockIdx.y * wv.nchunksA * NBP;
+  int ca_b = a_off / wv.CA, rem_b = a_off % wv.CA;  // analysis chunk of frame a, and a's position inside it
+#endif
   for (int bi = 0; bi < nbatch; ++bi) {
     const int fb = bi * G;                       // frame index relative to a
     const int nfr = min(G, nfr_total - fb);      // frames present in this batch
@@ -743,8 +747,11 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     //      real pair -> Z[0]); it also folds the self-paired bin NC/2 (its slot 8, staged at 0).
     C x[16];
     if (g < nfr) {
-      const int ca = (a_off + fb + g) / wv.CA;  // analysis chunk of this frame: its phase prefix row (L1-resident)
-      const uint32_t* pp = sc.pre + ((size_t)blockIdx.y * wv.nchunksA + ca) * NBP;
+      // analysis chunk of this frame -> its phase prefix row (L1-resident).  The chunk index of the batch's first
+      // frame is carried along (ca_b, rem_b): no division per frame
+      int ca = ca_b;
+      for (int r = rem_b + g; r >= wv.CA; r -= wv.CA) ++ca;  // (at most one step unless the chunks are shorter than a batch)
+      const uint32_t* pp = pre_trk + (size_t)ca * NBP;
       const uint2* src = s_rec + g * NBP;
       C* zb = buf + g * BUF;
       constexpr SpecRot32 rot = spec_rot32();
@@ -979,6 +986,13 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
       }
     }
     __syncthreads();
+#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
+    rem_b += G;
+    while (rem_b >= wv.CA) {
+      rem_b -= wv.CA;
+      ++ca_b;
+    }
+#endif
   }
   // hops whose later frames do not exist (end of the track): what has been summed is the result
   const int last = nfr_total - 1;
