@@ -1,6 +1,6 @@
 // tools/ubench/fp32x2_probe.cu -- issue rate of the packed single-precision instructions of sm_100a
 // (FADD2 / FMUL2 / FFMA2) against their scalar forms, alone and mixed with integer work.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/fp32x2_probe tools/ubench/fp32x2_probe.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o variants/fp32x2_probe tools/ubench/fp32x2_probe.cu   (variants/ ships to the GPU box)
 // Prints warp-instructions per clock per SM sub-partition for each loop body.
 #include <cstdio>
 #include <cuda_runtime.h>
