@@ -89,6 +89,13 @@ int ensure_tables(mlx_ctx* c, int N, bool want_pv, Tables** out) {
       const double a = 2.0 * M_PI * (double)k / (double)N;
       twrd[k] = cplx<double>{std::cos(a), -std::sin(a)};
     }
+    // powers of the second FFT stage's twiddle, exp(-2 pi i k r / 256) (fft.cuh: twiddle_table16)
+    std::vector<cplx<double>> tw1d(15 * 16);
+    for (int r = 1; r < 16; ++r)
+      for (int k = 0; k < 16; ++k) {
+        const double a = 2.0 * M_PI * (double)(k * r) / 256.0;
+        tw1d[(r - 1) * 16 + k] = cplx<double>{std::cos(a), -std::sin(a)};
+      }
     // PV-spec A.1: periodic Hann computed in double, stored as float; A.7: g = H / sum w^2 (float)
     std::vector<float> win(N), wsyn(N);
     std::vector<double> wind(N);
@@ -103,6 +110,7 @@ int ensure_tables(mlx_ctx* c, int N, bool want_pv, Tables** out) {
     int rc;
     if ((rc = upload_vec(tb.tw_d, twd, c->stream))) return rc;
     if ((rc = upload_vec(tb.twr_d, twrd, c->stream))) return rc;
+    if ((rc = upload_vec(tb.tw1_d, tw1d, c->stream))) return rc;
     if ((rc = upload_vec(tb.win, win, c->stream))) return rc;
     if ((rc = upload_vec(tb.win_d, wind, c->stream))) return rc;
     if ((rc = upload_vec(tb.wsyn, wsyn, c->stream))) return rc;
@@ -297,7 +305,7 @@ int pv_launch(mlx_ctx* c, const mlx_pv_params* p, const PvPlan& pl, const PvPrep
   PvTables pt{static_cast<const cplx<double>*>(tb->tw_d.p), static_cast<const cplx<double>*>(tb->twr_d.p),
               static_cast<const cplx<float>*>(tb->tw_f.p),  static_cast<const cplx<float>*>(tb->twr_f.p),
               static_cast<const float*>(tb->win.p),         static_cast<const double*>(tb->win_d.p),
-              static_cast<const float*>(tb->wsyn.p)};
+              static_cast<const float*>(tb->wsyn.p),        static_cast<const cplx<double>*>(tb->tw1_d.p)};
   PvScratch sc{static_cast<uint2*>(c->stage.p), static_cast<uint32_t*>(c->tot.p),
                static_cast<uint32_t*>(c->totc.p), static_cast<uint32_t*>(c->pre.p),
                pr.carry + (size_t)first * pl.NBP};
@@ -420,7 +428,7 @@ void mlx_destroy(mlx_ctx* c) {
     b->release();
   for (auto& kv : c->tables)
     for (DevBuf* b : {&kv.second.tw_d, &kv.second.twr_d, &kv.second.tw_f, &kv.second.twr_f, &kv.second.win,
-                      &kv.second.win_d, &kv.second.wsyn, &kv.second.decay})
+                      &kv.second.win_d, &kv.second.wsyn, &kv.second.decay, &kv.second.tw1_d})
       b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (auto& s : c->slots) {

@@ -44,7 +44,7 @@ struct DevBuf {
 };
 
 struct Tables {
-  DevBuf tw_d, twr_d, tw_f, twr_f, win, win_d, wsyn, decay;
+  DevBuf tw_d, twr_d, tw_f, twr_f, win, win_d, wsyn, decay, tw1_d;
   bool pv_ready = false, spec_ready = false;
 };
 

@@ -254,6 +254,30 @@ MLX_HD void twiddle_powers(cplx<T> (&v)[R], const cplx<T> w) {
   }
 }
 
+// v[r] *= tab[(r - 1) * 16 + k], r = 1..15: the fifteen powers of the second stage's twiddle exp(DIR 2 pi i k / 256)
+// from a 240-entry table (k < 16) instead of a chain of fourteen complex products.  Used by the double-precision
+// analysis transform, where the chain is 56 dependent FP64 instructions per thread and frame; the table values are
+// correctly rounded, the chain drifts by a few ulp.
+template <typename T>
+MLX_HD void twiddle_table16(cplx<T> (&v)[16], const cplx<T>* tab, int k) {
+#pragma unroll
+  for (int r = 1; r < 16; ++r) {
+#ifdef __CUDA_ARCH__
+    cplx<T> w;
+    if constexpr (sizeof(T) == 8) {
+      const double2 q = __ldg(reinterpret_cast<const double2*>(tab + (r - 1) * 16 + k));
+      w = cplx<T>{(T)q.x, (T)q.y};
+    } else {
+      const float2 q = __ldg(reinterpret_cast<const float2*>(tab + (r - 1) * 16 + k));
+      w = cplx<T>{(T)q.x, (T)q.y};
+    }
+#else
+    const cplx<T> w = tab[(r - 1) * 16 + k];
+#endif
+    v[r] = cmul(v[r], w);
+  }
+}
+
 // ---------------------------------------------------------------- plan
 template <int NC>
 struct FftPlan {
@@ -290,16 +314,21 @@ struct FftPlan {
 // PRE1: also keep the 15 powers of the stage-1 twiddle (radix-16 second stage, one butterfly per
 // thread) in registers instead of rebuilding them per transform -- the same product tree, so the
 // results are bit-identical; costs 30 registers, saves 14 complex products per transform.
-template <typename T, int NC, int DIR, bool PRE1 = false>
+// TAB1: the powers of the stage-1 twiddle come from `tab1` (twiddle_table16; forward direction only: the table holds
+// exp(-2 pi i k r / 256)), the stage-1 twiddle register is not kept.
+template <typename T, int NC, int DIR, bool PRE1 = false, bool TAB1 = false>
 struct FftTwiddles {
   using P = FftPlan<NC>;
   static constexpr bool kPre1 = PRE1 && P::NSTAGES >= 2 && P::radix(1) == 16 && sizeof(T) == 4;
+  static constexpr bool kTab1 = TAB1 && P::NSTAGES >= 2 && P::radix(1) == 16 && DIR < 0;
   cplx<T> w[P::NW];
   cplx<T> p1[kPre1 ? 15 : 1];
+  const cplx<T>* tab1 = nullptr;
   MLX_HD void init(int t, const cplx<T>* table) {
 #pragma unroll
     for (int s = 1; s < P::NSTAGES; ++s) {
       const int R = P::radix(s), NS = P::ns(s), BPT = 16 / R;
+      if (kTab1 && s == 1) continue;  // read from the table
 #pragma unroll
       for (int b = 0; b < BPT; ++b) {
         const int j = t + b * P::TPF;
@@ -354,7 +383,9 @@ struct Fft {
       C v[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = x[b + r * BPT];
-      if constexpr (S == 1 && TW::kPre1) {
+      if constexpr (S == 1 && TW::kTab1) {
+        twiddle_table16(v, tw.tab1, (t + b * TPF) & (NS - 1));
+      } else if constexpr (S == 1 && TW::kPre1) {
 #pragma unroll
         for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw.p1[r - 1]);
       } else if constexpr (S > 0 && LAST && MLX_FFT_DERIVE_LAST && BPT > 1 && sizeof(T) == 8) {

@@ -34,6 +34,7 @@ struct PvTables {
   const float* win;           // periodic Hann, float, [fftN]
   const double* win_d;        // the same float values widened to double (exact), [fftN]
   const float* wsyn;          // gain * win / fftN  (synthesis window incl. irfft 1/N), [fftN]
+  const cplx<double>* tw1_d;  // exp(-2 pi i k r / 256) at [(r - 1) * 16 + k], r = 1..15, k < 16 (fft.cuh: twiddle_table16)
 };
 
 // One wave = owned frame window [wb, we) of every track; intermediates live in `rows` scratch rows

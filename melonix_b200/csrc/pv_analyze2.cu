@@ -40,6 +40,9 @@
 #include "kernels.h"
 #include "pv_analysis.cuh"
 #include "pv_common.cuh"
+#ifndef MLX_KA_TAB1
+#define MLX_KA_TAB1 1
+#endif
 #include "pv_shift.cuh"
 #include "tma.cuh"
 
@@ -80,6 +83,7 @@ struct Ka2Cfg {
 // the FFT role's only twiddle register (shape expected by Fft<>::compute)
 struct Ka2Twiddle {
   static constexpr bool kPre1 = false;
+  static constexpr bool kTab1 = false;  // (this kernel applies the stage-1 table itself)
   cplx<double> w[1];
 };
 
@@ -274,7 +278,11 @@ pv_analyze2_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const Pv
       bar.sync();
       F::load(x, fb, t);
       bar.sync();  // every load of the group done before the linear stores overwrite the padded slots
+#if MLX_KA_TAB1
+      twiddle_table16(x, tb.tw1_d, t & 15);  // as the general kernel (bit-identical results)
+#else
       twiddle_powers<16>(x, tw1.w[0]);
+#endif
       dft16<-1>(x);
       const int k = t & 15;
       C* p = fb + (t - k) * 16 + k;  // stage-1 butterfly t writes elements (t-k)*16 + k + 16 r

@@ -221,8 +221,13 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
     tma_load_1d(tile, tr.x + (a - 4) * H, TILE * sizeof(float), mbar);
   }
 
-  FftTwiddles<double, NC, -1> twd;
+#ifndef MLX_KA_TAB1
+#define MLX_KA_TAB1 1  // stage-1 twiddle powers of the FP64 transform from a 240-entry table (L1) instead of a chain of
+                       // fourteen dependent complex products per thread and frame
+#endif
+  FftTwiddles<double, NC, -1, false, MLX_KA_TAB1 != 0> twd;
   twd.init(t, tb.tw_d);
+  twd.tab1 = tb.tw1_d;
   // pair slots: bins k and NC-k for k = 1 + tid + q*THREADS <= NC/2; thread 0 also owns (0, NC)
   C wpair[QP];  // exp(-2 pi i k / N) of this thread's pairs
 #pragma unroll
