@@ -41,7 +41,7 @@
 #include "pv_analysis.cuh"
 #include "pv_common.cuh"
 #ifndef MLX_KA_TAB1
-#define MLX_KA_TAB1 1
+#define MLX_KA_TAB1 0
 #endif
 #include "pv_shift.cuh"
 #include "tma.cuh"

@@ -222,8 +222,9 @@ pv_analyze_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
   }
 
 #ifndef MLX_KA_TAB1
-#define MLX_KA_TAB1 1  // stage-1 twiddle powers of the FP64 transform from a 240-entry table (L1) instead of a chain of
-                       // fourteen dependent complex products per thread and frame
+#define MLX_KA_TAB1 0  // 1: stage-1 twiddle powers of the FP64 transform from a 240-entry table (L1) instead of a chain of
+                       // fourteen dependent complex products per thread and frame -- measured: 13.83 ms against 13.20
+                       // (fifteen 16-byte L1 loads per thread cost more than the 56 FP64 instructions they replace)
 #endif
   FftTwiddles<double, NC, -1, false, MLX_KA_TAB1 != 0> twd;
   twd.init(t, tb.tw_d);
