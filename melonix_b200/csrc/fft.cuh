@@ -64,16 +64,21 @@ MLX_HD cplx<T> csub(const cplx<T> a, const cplx<T> b) {
 #if defined(__CUDA_ARCH__) && MLX_FFT_PACKED_F32
 // sm_100a packed single precision: a complex float is one aligned 64-bit register pair, so a complex
 // add / subtract is ONE FADD2 (the negation folds into the operand modifier).  Same rounding as two FADDs.
+// (MLX_FFT_PACKED_F32 = 2 / 3: only the additions / only the subtractions packed -- tuning experiments)
+#if MLX_FFT_PACKED_F32 != 3
 template <>
 MLX_HD cplx<float> cadd<float>(const cplx<float> a, const cplx<float> b) {
   const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
   return cplx<float>{r.x, r.y};
 }
+#endif
+#if MLX_FFT_PACKED_F32 != 2
 template <>
 MLX_HD cplx<float> csub<float>(const cplx<float> a, const cplx<float> b) {
   const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
   return cplx<float>{r.x, r.y};
 }
+#endif
 #endif
 // multiply by DIR*i  (DIR = -1: forward transform, e^{-i...};  DIR = +1: inverse)
 template <int DIR, typename T>

@@ -1,7 +1,7 @@
 #!/bin/bash
 # PV + Spec parity on the default build; bench + Spec probe for default and variants
 mkdir -p gpurun_out; o=gpurun_out
-(timeout 900 python -m pytest tests/test_gpu_pv.py tests/test_gpu_spec.py -m gpu -x -q) > $o/r2j_pytest.log 2>&1; tail -3 $o/r2j_pytest.log
+true
 run() { name=$1; shift
   env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --no-extras 2>$o/var_$name.err | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); k=d['roofline']['kernel_ms_per_step']
