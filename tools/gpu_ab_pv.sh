@@ -1,5 +1,7 @@
 #!/bin/bash
-# PV parity tests, resident bench, and a short ncu metrics pass (shared-memory wavefronts / conflicts) of the PV kernels
+# A/B on one B200: PV parity tests on the default build, the resident bench for the default build and for variants/NAME.so
+# (tools/build_variant.sh), then a short ncu metrics pass (time, instructions, shared-memory wavefronts and conflicts,
+# L1 data pipe, issue slots) of the PV kernels
 mkdir -p gpurun_out; o=gpurun_out
 (timeout 900 python -m pytest tests/test_gpu_pv.py -m gpu -x -q) > $o/r2e_pytest.log 2>&1; tail -3 $o/r2e_pytest.log
 run() { name=$1; shift
