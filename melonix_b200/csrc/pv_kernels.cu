@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "fft.cuh"
 #include "kernels.h"
@@ -1014,6 +1015,287 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
 }
 
 // ------------------------------------------------------------------------------------------------
+// K_S32: the synthesis kernel with THIRTY-TWO points per thread, for fftN = 2048 (NC = 1024 = 32 x 32).
+// One warp transforms one frame in two radix-32 stages with ONE exchange through shared memory (the 16-point plan
+// needs two: 16 x 16 x 4), synchronised by __syncwarp alone; the 31 powers of the second stage's twiddle stay in
+// registers for the whole kernel (exact table values, no power tree per frame).  CTA = 4 warps = 4 frames, three
+// CTAs per SM at up to 168 registers.  Fold, record staging by TMA, overlap-add and output are those of
+// pv_synth_kernel with TPF = 32 (pairs k = t + 32 m, m < 16; mirrored bins staged at (16 - m)*32 - t).
+#ifndef MLX_KS32
+#define MLX_KS32 1
+#endif
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+MLX_HDC double ks32_cos(double x) {
+  double term = 1.0, sum = 1.0;
+  for (int i = 1; i < 24; ++i) {
+    term *= -x * x / ((2 * i - 1) * (2 * i));
+    sum += term;
+  }
+  return sum;
+}
+MLX_HDC double ks32_sin(double x) {
+  double term = x, sum = x;
+  for (int i = 1; i < 24; ++i) {
+    term *= -x * x / ((2 * i) * (2 * i + 1));
+    sum += term;
+  }
+  return sum;
+}
+struct Rot64 {  // exp(-2 pi i m / 64), m < 16  (c = cos, s = -sin)
+  float c[16], s[16];
+};
+MLX_HDC Rot64 make_rot64() {
+  Rot64 r{};
+  for (int m = 0; m < 16; ++m) {
+    r.c[m] = (float)ks32_cos(kTwoPi * m / 64.0);
+    r.s[m] = (float)-ks32_sin(kTwoPi * m / 64.0);
+  }
+  return r;
+}
+struct W32Tab {  // exp(+2 pi i k / 32), k < 16
+  float c[16], s[16];
+};
+MLX_HDC W32Tab make_w32() {
+  W32Tab r{};
+  for (int k = 0; k < 16; ++k) {
+    r.c[k] = (float)ks32_cos(kTwoPi * k / 32.0);
+    r.s[k] = (float)ks32_sin(kTwoPi * k / 32.0);
+  }
+  return r;
+}
+// 32-point DFT with e^{+i...} (inverse direction), natural order in and out: two interleaved 16-point
+// transforms and one radix-2 level
+__device__ __forceinline__ void idft32(cplx<float> (&v)[32]) {
+  using C = cplx<float>;
+  C e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    e[i] = v[2 * i];
+    o[i] = v[2 * i + 1];
+  }
+  dft16<+1>(e);
+  dft16<+1>(o);
+  constexpr W32Tab w = make_w32();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    C tw;
+    if (k == 0) tw = o[k];
+    else if (k == 8) tw = C{-o[k].y, o[k].x};  // * (+i)
+    else tw = C{o[k].x * w.c[k] - o[k].y * w.s[k], o[k].x * w.s[k] + o[k].y * w.c[k]};
+    v[k] = cadd(e[k], tw);
+    v[k + 16] = csub(e[k], tw);
+  }
+}
+MLX_HDC int pad32(int i) { return i + (i >> 5); }
+
+template <int N, bool O16>
+__global__ void __launch_bounds__(128, 3)
+pv_synth32_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
+  constexpr int NC = N / 2, TPF = 32, G = 4, THREADS = 128, H = N / 4, H2 = H / 2, NBP = NC + 32;
+  constexpr int BUF = NC + NC / 32;
+  constexpr int COLS = H2 / THREADS;
+  static_assert(NC == 1024, "two radix-32 stages");
+  using C = cplx<float>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  C* buf = reinterpret_cast<C*>(smem_raw);  // [G][BUF]
+  uint2* s_rec = reinterpret_cast<uint2*>(buf + G * BUF);  // [G][NBP]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rec + G * NBP);
+
+  const int tid = threadIdx.x;
+  const int g = tid >> 5, t = tid & 31;
+  const PvTrack tr = tracks[blockIdx.y];
+  if (O16 ? (tr.out16 == nullptr) : (tr.out == nullptr)) return;
+  const long long hop_lim = min(wv.we, tr.F);
+  const long long a = wv.wb + (long long)blockIdx.x * wv.CS;
+  if (a >= hop_lim) return;
+  const long long b = min(a + (long long)wv.CS, hop_lim);
+  const long long flim = min(b + 3, tr.F);  // frames [a, flim) contribute to hops [a, b)
+
+  // powers of the second stage's twiddle exp(+2 pi i t / NC): exact table values, kept for the whole kernel
+  C p1[31];
+#pragma unroll
+  for (int r = 1; r < 32; ++r) {
+    const float2 q = __ldg(reinterpret_cast<const float2*>(tb.tw_f + ((t * r) & (NC - 1))));  // exp(-2 pi i t r / NC)
+    p1[r - 1] = C{q.x, -q.y};
+  }
+  const float2 wf0v = __ldg(reinterpret_cast<const float2*>(tb.twr_f + t));  // exp(-2 pi i t / N)
+  const C wf0{wf0v.x, wf0v.y};
+
+  const int nbatch = (int)((flim - a + G - 1) / G);
+  const int nfr_total = (int)(flim - a);
+  const int nhop = (int)(b - a);
+  const size_t row0 = (size_t)blockIdx.y * wv.rows + (size_t)(a - wv.wb);
+  const int a_off = (int)(a - wv.wb);
+  float2 p0[COLS], pa[COLS], pb[COLS];  // pending overlap-add sums of the three youngest hops
+  float2 wq[COLS][4];                   // synthesis window at this thread's columns, quarter q of the frame
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    p0[c] = pa[c] = pb[c] = make_float2(0.f, 0.f);
+    const int i2 = tid + c * THREADS;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wq[c][q] = __ldg(reinterpret_cast<const float2*>(tb.wsyn + q * H + 2 * i2));
+  }
+  auto emit_hop = [&](int hrel, int i2, float2 v) {  // hop `hrel` (relative to a) of column i2, if this chunk owns it
+    if (hrel >= 0 && hrel < nhop) {
+      const long long o = (a + hrel) * H + 2 * i2;
+      if constexpr (O16) {
+        if (o + 1 < tr.n) *reinterpret_cast<short2*>(tr.out16 + o) = make_short2(pcm16(v.x), pcm16(v.y));
+        else if (o < tr.n) tr.out16[o] = pcm16(v.x);
+      } else {
+        if (o + 1 < tr.n) *reinterpret_cast<float2*>(tr.out + o) = v;
+        else if (o < tr.n) tr.out[o] = v.x;
+      }
+    }
+  };
+  const bool interior = b * H <= tr.n;
+  float* const pout = O16 ? nullptr : tr.out + a * H + 2 * tid;
+  short* const pout16 = O16 ? tr.out16 + a * H + 2 * tid : nullptr;
+  const uint2* const pst = sc.stage + row0 * NBP;
+  if (tid == 0) mbar_init(mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)min(G, nfr_total) * NBP * (uint32_t)sizeof(uint2);
+    mbar_expect_tx(mbar, bytes);
+    tma_load_1d(s_rec, pst, bytes, mbar);
+  }
+  const uint32_t* const pre_trk = sc.pre + (size_t)blockIdx.y * wv.nchunksA * NBP;
+  int ca_b = a_off / wv.CA, rem_b = a_off % wv.CA;  // analysis chunk of frame a, and a's position inside it
+
+  for (int bi = 0; bi < nbatch; ++bi) {
+    const int fb = bi * G;
+    const int nfr = min(G, nfr_total - fb);
+    mbar_wait(mbar, bi & 1);
+    float* const pob = pout + (long long)(fb - 3) * H;
+    short* const pob16 = pout16 + (long long)(fb - 3) * H;
+    C x[32];
+    C* const zb = buf + g * BUF;
+    if (g < nfr) {
+      int ca = ca_b;
+      for (int r = rem_b + g; r >= wv.CA; r -= wv.CA) ++ca;
+      const uint32_t* pp = pre_trk + (size_t)ca * NBP;
+      const uint2* src = s_rec + g * NBP;
+      constexpr Rot64 rot = make_rot64();
+      auto fold = [&](uint2 rk, uint2 rm, uint32_t pk, uint32_t pm, C w, C& zk, C& zm) {
+        float sk, ck, sm, cm;
+        sincos_turns(pk + rk.y, sk, ck);
+        sincos_turns(pm + rm.y, sm, cm);
+        const float mkq = __uint_as_float(rk.x), mmq = __uint_as_float(rm.x);
+        const float ykr = mkq * ck, yki = mkq * sk, ymr = mmq * cm, ymi = mmq * sm;
+        const float er = ykr + ymr, ei = yki - ymi;
+        const float dr = ykr - ymr, di = yki + ymi;
+        const float orr = dr * w.x + di * w.y, oi = di * w.x - dr * w.y;
+        zk = C{er - oi, ei + orr};
+        zm = C{er + oi, orr - ei};
+      };
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int k = t + m * TPF, mbin = NC - k;
+        const uint2 rk = src[k], rm = src[mbin];
+        const uint32_t pk = __ldg(pp + k), pm = __ldg(pp + mbin);
+        C w = wf0;  // exp(-2 pi i k / N) = w0 * exp(-2 pi i m / 64)
+        if (m != 0)
+          w = C{fmaf(-wf0.y, rot.s[m], spec_mul_here(wf0.x, rot.c[m])), fmaf(wf0.y, rot.c[m], spec_mul_here(wf0.x, rot.s[m]))};
+        C zk, zm;
+        fold(rk, rm, pk, pm, w, zk, zm);
+        int idx = (16 - m) * TPF - t;
+        if (m == 0 && t == 0) {  // DC / Nyquist (Im forced to 0) and the self-paired bin NC/2 (slot 16 of thread 0)
+          float s0, c0, sn, cn;
+          sincos_turns(pk + rk.y, s0, c0);
+          sincos_turns(pm + rm.y, sn, cn);
+          const float y0 = __uint_as_float(rk.x) * c0, yn = __uint_as_float(rm.x) * cn;
+          zk = C{y0 + yn, y0 - yn};
+          const uint2 rh = src[NC / 2];
+          const uint32_t ph = __ldg(pp + NC / 2);
+          const float2 wh = __ldg(reinterpret_cast<const float2*>(tb.twr_f + NC / 2));
+          C zdummy;
+          fold(rh, rh, ph, ph, C{wh.x, wh.y}, zm, zdummy);
+          idx = 0;
+        }
+        x[m] = zk;
+        zb[idx] = zm;
+      }
+    }
+    __syncthreads();  // records consumed, staged halves visible
+    if (tid == 0 && bi + 1 < nbatch) {
+      const uint32_t bytes = (uint32_t)min(G, nfr_total - (fb + G)) * NBP * (uint32_t)sizeof(uint2);
+      fence_proxy_async();
+      mbar_expect_tx(mbar, bytes);
+      tma_load_1d(s_rec, pst + (size_t)(fb + G) * NBP, bytes, mbar);
+    }
+    if (g < nfr) {
+#pragma unroll
+      for (int m = 16; m < 32; ++m) x[m] = zb[(m - 16) * TPF + t];
+      __syncwarp();  // the staging area is overwritten by the first stage's stores
+      idft32(x);     // stage 0: butterfly t on slots x[r] = Z[t + 32 r]; output r goes to position 32 t + r
+      {
+        C* p = zb + 33 * t;  // pad32(32 t + r) = 33 t + r
+#pragma unroll
+        for (int r = 0; r < 32; ++r) p[r] = x[r];
+      }
+      __syncwarp();
+      {
+        const C* p = zb + t;  // pad32(t + 32 r) = t + 33 r
+#pragma unroll
+        for (int r = 0; r < 32; ++r) x[r] = p[33 * r];
+      }
+#pragma unroll
+      for (int r = 1; r < 32; ++r) x[r] = cmul(x[r], p1[r - 1]);
+      idft32(x);  // stage 1: output r is element t + 32 r (natural order, the slots this thread has just read)
+      {
+        C* p = zb + t;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) p[33 * r] = x[r];
+      }
+    }
+    __syncthreads();
+
+    // overlap-add as in pv_synth_kernel (window applied here, fixed ascending-frame order)
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const int i2 = tid + c * THREADS;
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        if (gi < nfr) {
+          const C* yb = buf + gi * BUF;
+          const C q0 = yb[pad32(i2)], q1 = yb[pad32(H2 + i2)];
+          const C q2 = yb[pad32(2 * H2 + i2)], q3 = yb[pad32(3 * H2 + i2)];
+          const float2 o = make_float2(fmaf(q0.x, wq[c][0].x, p0[c].x), fmaf(q0.y, wq[c][0].y, p0[c].y));
+          p0[c] = make_float2(fmaf(q1.x, wq[c][1].x, pa[c].x), fmaf(q1.y, wq[c][1].y, pa[c].y));
+          pa[c] = make_float2(fmaf(q2.x, wq[c][2].x, pb[c].x), fmaf(q2.y, wq[c][2].y, pb[c].y));
+          pb[c] = make_float2(q3.x * wq[c][3].x, q3.y * wq[c][3].y);
+          if (interior) {
+            const int hrel = fb + gi - 3;
+            if (hrel >= 0 && hrel < nhop) {
+              if constexpr (O16)
+                *reinterpret_cast<short2*>(pob16 + gi * H + 2 * c * THREADS) = make_short2(pcm16(o.x), pcm16(o.y));
+              else
+                *reinterpret_cast<float2*>(pob + gi * H + 2 * c * THREADS) = o;
+            }
+          } else {
+            emit_hop(fb + gi - 3, i2, o);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    rem_b += G;
+    while (rem_b >= wv.CA) {
+      rem_b -= wv.CA;
+      ++ca_b;
+    }
+  }
+  const int last = nfr_total - 1;
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    const int i2 = tid + c * THREADS;
+    emit_hop(last - 2, i2, p0[c]);
+    emit_hop(last - 1, i2, pa[c]);
+    emit_hop(last, i2, pb[c]);
+  }
+}
+constexpr size_t kSmemS32 = sizeof(cplx<float>) * 4 * (1024 + 32) + sizeof(uint2) * 4 * (1024 + 32) + 64;
+
+// ------------------------------------------------------------------------------------------------
 template <int N>
 static cudaError_t configure_n() {
   constexpr int G = PvG<N>::value, GA = PvG<N>::analyze;
@@ -1029,8 +1311,15 @@ static cudaError_t configure_n() {
   e = cudaFuncSetAttribute(pv_synth_kernel<N, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)PvCfg<N, G>::SMEM_S);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(pv_synth_kernel<N, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)PvCfg<N, G>::SMEM_S);
+  e = cudaFuncSetAttribute(pv_synth_kernel<N, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)PvCfg<N, G>::SMEM_S);
+  if (e != cudaSuccess) return e;
+  if constexpr (N == 2048 && MLX_KS32) {
+    e = cudaFuncSetAttribute(pv_synth32_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemS32);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(pv_synth32_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemS32);
+  }
+  return e;
 }
 
 #define MLX_PV_DISPATCH(N_, ...)                  \
@@ -1102,6 +1391,15 @@ cudaError_t launch_pv_scan(int fftN, int ntracks, const PvWave& wv, const PvScra
 
 cudaError_t launch_pv_synth(int fftN, const PvTrack* tracks, int ntracks, const PvWave& wv,
                             const PvTables& tb, const PvScratch& sc, bool out16, cudaStream_t st) {
+#if MLX_KS32
+  static const bool ks32 = getenv("MLX_PV_NO_KS32") == nullptr;  // (A/B switch; the 32-point plan is the default at 2048)
+  if (fftN == 2048 && ks32) {
+    dim3 grid(wv.nchunksS, ntracks);
+    if (out16) pv_synth32_kernel<2048, true><<<grid, 128, kSmemS32, st>>>(tracks, wv, tb, sc);
+    else pv_synth32_kernel<2048, false><<<grid, 128, kSmemS32, st>>>(tracks, wv, tb, sc);
+    return cudaGetLastError();
+  }
+#endif
   MLX_PV_DISPATCH(fftN, {
     constexpr int G = PvG<N>::value;
     dim3 grid(wv.nchunksS, ntracks);
