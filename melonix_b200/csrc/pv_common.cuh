@@ -8,12 +8,6 @@
 #include "fft.cuh"
 #include "kernels.h"
 
-#ifndef MLX_KS_WIN_SMEM
-#define MLX_KS_WIN_SMEM 0  // synthesis window in shared memory instead of 32 registers per thread
-#endif
-#ifndef MLX_KS_TMA
-#define MLX_KS_TMA 1  // K_S: the stage records of a batch arrive by one TMA bulk copy, issued a batch ahead
-#endif
 #ifndef MLX_KA_CTAS_MAXN
 #define MLX_KA_CTAS_MAXN 2048  // largest fftN analysed with MLX_KA_CTAS CTAs per SM (beyond: one 512-thread CTA)
 #endif
@@ -41,8 +35,7 @@ struct PvCfg {
   static constexpr int BUFS = BUF + 2;  // + the Nyquist bin's (mag, d) record + an all-zero record (empty K_j)
   static constexpr size_t SMEM_A = sizeof(cplx<double>) * G * BUFS + (WIN_D ? sizeof(double) * N : 0) +
                                    sizeof(float) * 2 * TILE + 64;
-  static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + (MLX_KS_WIN_SMEM ? sizeof(float) * N : 0) +
-                                   (MLX_KS_TMA ? sizeof(uint2) * G * NBP + 16 : 0) + 64;
+  static constexpr size_t SMEM_S = sizeof(cplx<float>) * G * BUF + sizeof(uint2) * G * NBP + 16 + 64;  // + stage records
 };
 
 // Frames per batch: synthesis keeps G*(N/2) = 4096 complex points in flight (256 threads, 2 CTAs per

@@ -52,9 +52,7 @@
 #define MLX_GATHER_V2 1  // constant-rate bin shift with frame-invariant constants (bit-identical to v1)
 #endif
 #ifndef MLX_KS_MINB3_MAXN
-#define MLX_KS_MINB3_MAXN 2048  // up to this fftN: three synthesis CTAs per SM (80 registers: no register prefetch
-                                // stage -- the records come from shared memory -- and the window through L1);
-                                // measured 5.88 -> 5.71 ms on the bench batch.  Beyond: two CTAs, window in registers.
+#define MLX_KS_MINB3_MAXN 2048  // up to this fftN: three synthesis CTAs per SM (80 registers), two beyond
 #endif
 #ifndef MLX_KS_PRE1
 #define MLX_KS_PRE1 0      // keep the 15 stage-1 twiddle powers of the inverse FFT in registers
@@ -592,45 +590,37 @@ pv_scan_kernel(int nb, int nbp, int nchunks, const PvScratch sc) {
 // the reference's export conversion (app.cpp:1209-1212): int16(x * 32767.), double product, truncation
 __device__ __forceinline__ short pcm16(float v) { return (short)__double2int_rz((double)v * 32767.); }
 
+// Three synthesis CTAs per SM up to MLX_KS_MINB3_MAXN (80 registers), two beyond.
 template <int N>
 struct KsTune {
-  static constexpr bool k3 = MLX_KS_TMA && !MLX_KS_WIN_SMEM && N <= MLX_KS_MINB3_MAXN;
-  static constexpr int MINB = k3 ? 3 : 2;      // synthesis CTAs per SM the register allocation is bounded for
-  static constexpr int GS = k3 ? 1 : 4;        // frames whose records are held in registers together
-  static constexpr bool WIN_LDG = k3;          // synthesis window through L1 (__ldg) instead of 32 registers
+  static constexpr int MINB = N <= MLX_KS_MINB3_MAXN ? 3 : 2;
 };
-#ifndef MLX_KS_FOLD_LOCAL
-#define MLX_KS_FOLD_LOCAL 1  // the synthesis spectrum of a frame is folded by the threads that transform it: thread t
-                             // builds its own slots k = t + m*TPF (m < 8) in registers and hands the mirrored bins
-                             // NC - k -- slot 15 - m of thread TPF - t -- over through an unpadded staging area.
-                             // Before, the pair threads wrote all of Z to shared memory (8-byte stores at k = 1 + tid:
-                             // every half-warp crosses a padding element, two-way conflicts) and the transform
-                             // loaded it back: 162 wavefronts per frame against 65 now, plus 32 for the phase
-                             // prefixes that no longer fit registers (L1 loads).  Needs MLX_KS_TMA.
-#endif
-#ifndef MLX_KS_WIN_OLA
-#define MLX_KS_WIN_OLA 1  // the synthesis window is applied by the overlap-add threads: a thread owns the same output
-                          // columns for every frame, so its 8 window factors per column live in registers for the whole
-                          // kernel and the product fuses into the overlap-add (FFMA).  Applied after the inverse FFT it
-                          // cost one 8-byte L1 load per two samples and frame: 65 of the ~760 wavefronts per frame of a
-                          // kernel that runs at 87 % of the L1 / shared-memory data pipe.
-#endif
 
+// How the kernel got here (each step measured, profiles/README.md):
+//  * the stage records of a batch (consecutive rows = one contiguous span) arrive by ONE TMA bulk copy issued while
+//    the previous batch is still in its inverse FFT / overlap-add (the global loads were 17 % of the stall samples);
+//  * the synthesis spectrum of a frame is folded by the threads that transform it: thread t builds its own slots
+//    k = t + m*TPF (m < 8) in registers and hands the mirrored bins NC - k -- slot 15 - m of thread TPF - t -- over
+//    through an unpadded staging area; phase prefixes come through L1 and twiddles by constant rotation (sixteen of
+//    each do not fit the 80 registers of three CTAs per SM).  Before, the pair threads wrote all of Z to shared memory
+//    and the transform loaded it back: 162 wavefronts per frame against 65 + 32;
+//  * the synthesis window is applied by the overlap-add threads: a thread owns the same output columns for every
+//    frame, so its 8 window factors per column live in registers and the product fuses into the sum (FFMA).
 template <int N, int G, bool O16>
 __global__ void __launch_bounds__(PvCfg<N, G>::THREADS, KsTune<N>::MINB)
 pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   using Cfg = PvCfg<N, G>;
   constexpr int NC = Cfg::NC, TPF = Cfg::TPF, H = Cfg::H, NBP = Cfg::NBP;
-  constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUF, QP = Cfg::QP;
+  constexpr int THREADS = Cfg::THREADS, BUF = Cfg::BUF;
   constexpr int H2 = H / 2;
   constexpr int COLS = (H2 + THREADS - 1) / THREADS;  // overlap-add columns (float2) per thread
-  constexpr int GS = G < KsTune<N>::GS ? G : KsTune<N>::GS;  // frames whose loads are in flight together
-  constexpr bool WIN_LDG = KsTune<N>::WIN_LDG;
   using C = cplx<float>;
   using F = Fft<float, NC, +1>;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  C* buf = reinterpret_cast<C*>(smem_raw);  // [G][BUF]
+  C* buf = reinterpret_cast<C*>(smem_raw);                                  // [G][BUF]
+  uint2* s_rec = reinterpret_cast<uint2*>(smem_raw + sizeof(C) * G * BUF);  // [G][NBP] stage records of the batch
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rec + G * NBP);
 
   const int tid = threadIdx.x;
   const int g = tid / TPF, t = tid % TPF;
@@ -644,55 +634,25 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
 
   FftTwiddles<float, NC, +1, MLX_KS_PRE1 != 0> twd;
   twd.init(t, tb.tw_f);
-#if MLX_KS_WIN_SMEM
-  float* s_wsyn = reinterpret_cast<float*>(buf + G * BUF);  // [N]
-  for (int i = tid; i < N; i += THREADS) s_wsyn[i] = tb.wsyn[i];
-  __syncthreads();
-#else
-  float wreg[(WIN_LDG || MLX_KS_WIN_OLA) ? 1 : 32];
-  if constexpr (!WIN_LDG && !MLX_KS_WIN_OLA) {
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const float2 w2 = *reinterpret_cast<const float2*>(tb.wsyn + 2 * (t + m * TPF));
-      wreg[2 * m] = w2.x;
-      wreg[2 * m + 1] = w2.y;
-    }
-  }
-#endif
-  C wr[QP];
-  uint32_t prek[QP], prem[QP];
-#pragma unroll
-  for (int q = 0; q < QP; ++q) {
-    const int k = 1 + tid + q * THREADS;
-    wr[q] = (k <= NC / 2) ? tb.twr_f[k] : C{1.f, 0.f};
-    prek[q] = prem[q] = 0u;
-  }
-  uint32_t pre0 = 0u, pren = 0u;
   const GroupBar<TPF> bar = make_group_bar<TPF>(g, tid);
-#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
   const float2 wf0v = __ldg(reinterpret_cast<const float2*>(tb.twr_f + t));  // exp(-2 pi i t / N)
   const C wf0{wf0v.x, wf0v.y};
-#endif
 
   const int nbatch = (int)((flim - a + G - 1) / G);
   const int nfr_total = (int)(flim - a);
   const int nhop = (int)(b - a);
   const size_t row0 = (size_t)blockIdx.y * wv.rows + (size_t)(a - wv.wb);
   const int a_off = (int)(a - wv.wb);
-  int next_chunk_at = 0;  // frame (relative to a) at which the analysis chunk, hence the prefix, changes
   float2 p0[COLS], p1[COLS], p2[COLS];  // pending overlap-add sums of the three youngest hops
-#pragma unroll
-  for (int c = 0; c < COLS; ++c) p0[c] = p1[c] = p2[c] = make_float2(0.f, 0.f);
-#if MLX_KS_WIN_OLA
   float2 wq[COLS][4];  // synthesis window (gain and 1/N included) at this thread's columns, quarter q of the frame
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
+    p0[c] = p1[c] = p2[c] = make_float2(0.f, 0.f);
     const int i2 = tid + c * THREADS;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       wq[c][q] = i2 < H2 ? __ldg(reinterpret_cast<const float2*>(tb.wsyn + q * H + 2 * i2)) : make_float2(0.f, 0.f);
   }
-#endif
   // hop `hrel` (relative to a) of column i2: written only if this chunk owns it
   auto emit_hop = [&](int hrel, int i2, float2 v) {
     if (hrel >= 0 && hrel < nhop) {
@@ -718,12 +678,6 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
   float* const pout = O16 ? nullptr : tr.out + a * H + 2 * tid;  // column 0 of this thread in hop a
   short* const pout16 = O16 ? tr.out16 + a * H + 2 * tid : nullptr;
   const uint2* const pst = sc.stage + row0 * NBP;
-#if MLX_KS_TMA
-  // The records of a batch (nfr consecutive rows = one contiguous span of the stage) arrive by ONE TMA bulk
-  // copy that is issued while the previous batch is still in its inverse FFT / overlap-add: the ~1 us
-  // latency of the global loads was the largest single stall of this kernel (17 % of the samples).
-  uint2* s_rec = reinterpret_cast<uint2*>(smem_raw + sizeof(C) * G * BUF + (MLX_KS_WIN_SMEM ? sizeof(float) * N : 0));
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_rec + G * NBP);
   if (tid == 0) mbar_init(mbar, 1);
   __syncthreads();
   if (tid == 0) {
@@ -731,22 +685,16 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
     mbar_expect_tx(mbar, bytes);
     tma_load_1d(s_rec, pst, bytes, mbar);
   }
-#endif
-
-#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
   const uint32_t* const pre_trk = sc.pre + (size_t)blockIdx.y * wv.nchunksA * NBP;
   int ca_b = a_off / wv.CA, rem_b = a_off % wv.CA;  // analysis chunk of frame a, and a's position inside it
-#endif
+
   for (int bi = 0; bi < nbatch; ++bi) {
     const int fb = bi * G;                       // frame index relative to a
     const int nfr = min(G, nfr_total - fb);      // frames present in this batch
-#if MLX_KS_TMA
     mbar_wait(mbar, bi & 1);
-#endif
     float* const pob = pout + (long long)(fb - 3) * H;  // hop fb - 3: where frame fb's first quarter completes
     short* const pob16 = pout16 + (long long)(fb - 3) * H;
 
-#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
     // ---- synthesis spectrum Y = smag e^{i theta} of frame fb + g, folded for the N/2-point complex inverse by
     //      the group that transforms it.  Pair (k, NC - k), k = t + m*TPF: Z[k] is slot m of this thread,
     //      Z[NC - k] slot 15 - m of thread TPF - t (slot 16 - m of thread 0 for t = 0): staged at
@@ -759,7 +707,7 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
       int ca = ca_b;
       for (int r = rem_b + g; r >= wv.CA; r -= wv.CA) ++ca;  // (at most one step unless the chunks are shorter than a batch)
       const uint32_t* pp = pre_trk + (size_t)ca * NBP;
-      const uint2* src = s_rec + g * NBP;
+      const uint2* src = s_rec + g * NBP;  // one 8-byte record per bin: .x = shifted magnitude, .y = chunk-local phase sum
       C* zb = buf + g * BUF;
       constexpr SpecRot32 rot = spec_rot32();
       auto fold = [&](uint2 rk, uint2 rm, uint32_t pk, uint32_t pm, C w, C& zk, C& zm) {
@@ -806,153 +754,27 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
         zb[idx] = zm;
       }
     }
-#else
-    // ---- synthesis spectrum Y = smag e^{i theta}, folded for the N/2-point complex inverse.
-    //      All global loads of a sub-batch are issued before the first use (latency hiding).
-#pragma unroll 1
-    for (int g0 = 0; g0 < nfr; g0 += GS) {
-      // one 8-byte record per bin: .x = shifted magnitude (float bits), .y = chunk-local phase sum
-      uint2 rk[GS][QP], rm[GS][QP], r0[GS], rn[GS];
-#if MLX_KS_TMA
-      auto fetch = [&](const uint2* src, int u) {  // shared memory: unit-stride 8-byte reads, conflict-free
-#pragma unroll
-        for (int q = 0; q < QP; ++q) {
-          const int k = 1 + tid + q * THREADS;
-          if (k <= NC / 2) {
-            rk[u][q] = src[k];
-            rm[u][q] = src[NC - k];
-          }
-        }
-        if (tid == 0) {
-          r0[u] = src[0];
-          rn[u] = src[NC];
-        }
-      };
-#pragma unroll
-      for (int u = 0; u < GS; ++u) fetch(s_rec + min(g0 + u, nfr - 1) * NBP, u);  // (clamped rows are never used)
-#else
-      auto fetch = [&](const uint2* src, int u) {
-#pragma unroll
-        for (int q = 0; q < QP; ++q) {
-          const int k = 1 + tid + q * THREADS;
-          if (k <= NC / 2) {
-            rk[u][q] = __ldg(src + k);
-            rm[u][q] = __ldg(src + NC - k);
-          }
-        }
-        if (tid == 0) {
-          r0[u] = __ldg(src);
-          rn[u] = __ldg(src + NC);
-        }
-      };
-      if (nfr == G) {  // full batch (all but the last of a chunk): rows at compile-time offsets
-        const uint2* src0 = pst + (size_t)(fb + g0) * NBP;
-#pragma unroll
-        for (int u = 0; u < GS; ++u) fetch(src0 + u * NBP, u);
-      } else {
-#pragma unroll
-        for (int u = 0; u < GS; ++u) {
-          const int gg = min(g0 + u, nfr - 1);  // clamp: duplicates of the last frame are never used
-          fetch(sc.stage + (row0 + fb + gg) * NBP, u);
-        }
-      }
-#endif
-#pragma unroll
-      for (int u = 0; u < GS; ++u) {
-        const int gg = g0 + u;
-        if (gg < nfr) {
-          if (fb + gg >= next_chunk_at) {  // entered the next analysis chunk: reload its phase prefix
-            const int ca = (a_off + fb + gg) / wv.CA;
-            next_chunk_at = (ca + 1) * wv.CA - a_off;
-            const uint32_t* pp = sc.pre + ((size_t)blockIdx.y * wv.nchunksA + ca) * NBP;
-#pragma unroll
-            for (int q = 0; q < QP; ++q) {
-              const int k = 1 + tid + q * THREADS;
-              if (k <= NC / 2) {
-                prek[q] = __ldg(pp + k);
-                prem[q] = __ldg(pp + NC - k);
-              }
-            }
-            if (tid == 0) {
-              pre0 = __ldg(pp);
-              pren = __ldg(pp + NC);
-            }
-          }
-          C* zb = buf + gg * BUF;
-#pragma unroll
-          for (int q = 0; q < QP; ++q) {
-            const int k = 1 + tid + q * THREADS;
-            if (k <= NC / 2) {
-              const int mbin = NC - k;
-              float sk, ck, sm, cm;
-              sincos_turns(prek[q] + rk[u][q].y, sk, ck);
-              sincos_turns(prem[q] + rm[u][q].y, sm, cm);
-              const float mkq = __uint_as_float(rk[u][q].x), mmq = __uint_as_float(rm[u][q].x);
-              const float ykr = mkq * ck, yki = mkq * sk, ymr = mmq * cm, ymi = mmq * sm;
-              // A = Y_k, B = conj(Y_m): E2 = A + B, D2 = A - B, O2 = D2 * conj(W^k)
-              const float er = ykr + ymr, ei = yki - ymi;
-              const float dr = ykr - ymr, di = yki + ymi;
-              const float orr = dr * wr[q].x + di * wr[q].y, oi = di * wr[q].x - dr * wr[q].y;
-              zb[fft_pad(k)] = C{er - oi, ei + orr};
-              if (mbin != k) zb[fft_pad(mbin)] = C{er + oi, orr - ei};
-            }
-          }
-          if (tid == 0) {  // Im of DC / Nyquist forced to 0
-            float s0, c0, sn, cn;
-            sincos_turns(pre0 + r0[u].y, s0, c0);
-            sincos_turns(pren + rn[u].y, sn, cn);
-            const float y0 = __uint_as_float(r0[u].x) * c0, yn = __uint_as_float(rn[u].x) * cn;
-            zb[0] = C{y0 + yn, y0 - yn};
-          }
-        }
-      }
-    }
-#endif
     __syncthreads();
-#if MLX_KS_TMA
     if (tid == 0 && bi + 1 < nbatch) {  // every thread has taken its records out of s_rec: refill for batch bi + 1
       const uint32_t bytes = (uint32_t)min(G, nfr_total - (fb + G)) * NBP * (uint32_t)sizeof(uint2);
       fence_proxy_async();
       mbar_expect_tx(mbar, bytes);
       tma_load_1d(s_rec, pst + (size_t)(fb + G) * NBP, bytes, mbar);
     }
-#endif
 
-    // ---- inverse FFT, synthesis window (includes gain and 1/N), result in place as real pairs
+    // ---- inverse FFT, result in place as real pairs (the synthesis window is applied by the overlap-add)
     if (g < nfr) {
       C* zb = buf + g * BUF;
-#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
 #pragma unroll
       for (int m = 8; m < 16; ++m) x[m] = zb[(m - 8) * TPF + t];  // the mirrored bins, staged by the partner thread
-#else
-      C x[16];
-      F::load(x, zb, t);
-#endif
       bar.sync();  // every thread of the group holds its inputs: the first stage may overwrite the buffer
       F::run(x, zb, t, twd, bar);
-#pragma unroll
-      for (int m = 0; m < (MLX_KS_WIN_OLA ? 0 : 16); ++m) {
-#if MLX_KS_WIN_SMEM
-        const float2 w2 = *reinterpret_cast<const float2*>(s_wsyn + 2 * (t + m * TPF));
-        x[m].x *= w2.x;
-        x[m].y *= w2.y;
-#else
-        if constexpr (WIN_LDG) {
-          const float2 w2 = __ldg(reinterpret_cast<const float2*>(tb.wsyn + 2 * (t + m * TPF)));  // 8 KB table: L1
-          x[m].x *= w2.x;
-          x[m].y *= w2.y;
-        } else {
-          x[m].x *= wreg[WIN_LDG ? 0 : 2 * m];
-          x[m].y *= wreg[WIN_LDG ? 0 : 2 * m + 1];
-        }
-#endif
-      }
       F::store(x, zb, t);
     }
     __syncthreads();
 
     // ---- overlap-add, atomics-free and in a fixed order.  Hop h = samples [hH, (h+1)H) is
-    //      ((y_h[3] + y_{h+1}[2]) + y_{h+2}[1]) + y_{h+3}[0]  (y_f[q] = quarter q of frame f).
+    //      ((y_h[3] + y_{h+1}[2]) + y_{h+2}[1]) + y_{h+3}[0]  (y_f[q] = windowed quarter q of frame f).
     //      Every thread owns output columns (float2 at 2*i2 inside the hop) for the whole chunk and
     //      keeps the three pending partial sums in registers; frames arrive in ascending order:
     //        emit hop f-3 = p0 + y_f[0];  p0 = p1 + y_f[1];  p1 = p2 + y_f[2];  p2 = y_f[3]
@@ -966,17 +788,10 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
             const C* yb = buf + gi * BUF;
             const C q0 = yb[fft_pad(i2)], q1 = yb[fft_pad(H2 + i2)];
             const C q2 = yb[fft_pad(2 * H2 + i2)], q3 = yb[fft_pad(3 * H2 + i2)];
-#if MLX_KS_WIN_OLA
             const float2 o = make_float2(fmaf(q0.x, wq[c][0].x, p0[c].x), fmaf(q0.y, wq[c][0].y, p0[c].y));
             p0[c] = make_float2(fmaf(q1.x, wq[c][1].x, p1[c].x), fmaf(q1.y, wq[c][1].y, p1[c].y));
             p1[c] = make_float2(fmaf(q2.x, wq[c][2].x, p2[c].x), fmaf(q2.y, wq[c][2].y, p2[c].y));
             p2[c] = make_float2(q3.x * wq[c][3].x, q3.y * wq[c][3].y);
-#else
-            const float2 o = make_float2(p0[c].x + q0.x, p0[c].y + q0.y);
-            p0[c] = make_float2(p1[c].x + q1.x, p1[c].y + q1.y);
-            p1[c] = make_float2(p2[c].x + q2.x, p2[c].y + q2.y);
-            p2[c] = make_float2(q3.x, q3.y);
-#endif
             if (interior) {
               const int hrel = fb + gi - 3;
               if (hrel >= 0 && hrel < nhop) {
@@ -993,13 +808,11 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
       }
     }
     __syncthreads();
-#if MLX_KS_FOLD_LOCAL && MLX_KS_TMA
     rem_b += G;
     while (rem_b >= wv.CA) {
       rem_b -= wv.CA;
       ++ca_b;
     }
-#endif
   }
   // hops whose later frames do not exist (end of the track): what has been summed is the result
   const int last = nfr_total - 1;
