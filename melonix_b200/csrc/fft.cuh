@@ -283,6 +283,97 @@ MLX_HD void twiddle_table16(cplx<T> (&v)[16], const cplx<T>* tab, int k) {
   }
 }
 
+// ---------------------------------------------------------------- 32 points per thread (NC = 1024 = 32 x 32)
+// cos / sin as compile-time constants (Taylor series in double; |x| <= 2 pi)
+MLX_HDC double fft_ccos(double x) {
+  double term = 1.0, sum = 1.0;
+  for (int i = 1; i < 28; ++i) {
+    term *= -x * x / ((2 * i - 1) * (2 * i));
+    sum += term;
+  }
+  return sum;
+}
+MLX_HDC double fft_csin(double x) {
+  double term = x, sum = x;
+  for (int i = 1; i < 28; ++i) {
+    term *= -x * x / ((2 * i) * (2 * i + 1));
+    sum += term;
+  }
+  return sum;
+}
+struct W32Tab {  // exp(+2 pi i k / 32), k < 16
+  float c[16], s[16];
+};
+MLX_HDC W32Tab make_w32() {
+  W32Tab r{};
+  for (int k = 0; k < 16; ++k) {
+    r.c[k] = (float)fft_ccos(6.283185307179586476925286766559 * k / 32.0);
+    r.s[k] = (float)fft_csin(6.283185307179586476925286766559 * k / 32.0);
+  }
+  return r;
+}
+// 32-point DFT, natural order in and out: two interleaved 16-point transforms and one radix-2 level
+template <int DIR>
+MLX_HD void dft32(cplx<float> (&v)[32]) {
+  using C = cplx<float>;
+  C e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    e[i] = v[2 * i];
+    o[i] = v[2 * i + 1];
+  }
+  dft16<DIR>(e);
+  dft16<DIR>(o);
+  constexpr W32Tab w = make_w32();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    C tw;  // o[k] * exp(DIR 2 pi i k / 32)
+    if (k == 0) {
+      tw = o[k];
+    } else if (k == 8) {
+      tw = cmul_i<DIR>(o[k]);
+    } else {
+      const float sn = DIR > 0 ? w.s[k] : -w.s[k];
+      tw = C{o[k].x * w.c[k] - o[k].y * sn, o[k].x * sn + o[k].y * w.c[k]};
+    }
+    v[k] = cadd(e[k], tw);
+    v[k + 16] = csub(e[k], tw);
+  }
+}
+// one pad element per 32: the stride-33 stores of the first radix-32 stage and the unit-stride loads of the
+// second are conflict-free
+MLX_HDC int pad32(int i) { return i + (i >> 5); }
+
+// The 1024-point transform of one frame by 32 threads (one warp), 32 points each: x[r] = in[t + 32 r] on entry and
+// out[t + 32 r] on return.  p1[r - 1] = exp(DIR 2 pi i t r / 1024), r = 1..31 (kept in registers by the caller).
+// `sync()` orders the group's shared-memory accesses (__syncwarp on the device; the host emulation runs the two halves
+// as separate passes over the threads).
+struct Fft32x32 {
+  using C = cplx<float>;
+  static constexpr int NC = 1024, BUF = NC + NC / 32;
+  template <int DIR>
+  static MLX_HD void stage0(C (&x)[32], C* buf, int t) {  // butterfly t; output r goes to position 32 t + r
+    dft32<DIR>(x);
+    C* p = buf + 33 * t;  // pad32(32 t + r) = 33 t + r
+#pragma unroll
+    for (int r = 0; r < 32; ++r) p[r] = x[r];
+  }
+  template <int DIR>
+  static MLX_HD void stage1(C (&x)[32], const C* buf, int t, const C (&p1)[31]) {
+    const C* p = buf + t;  // pad32(t + 32 r) = t + 33 r
+#pragma unroll
+    for (int r = 0; r < 32; ++r) x[r] = p[33 * r];
+#pragma unroll
+    for (int r = 1; r < 32; ++r) x[r] = cmul(x[r], p1[r - 1]);
+    dft32<DIR>(x);  // output r is element t + 32 r
+  }
+  static MLX_HD void store(const C (&x)[32], C* buf, int t) {  // natural order, padded
+    C* p = buf + t;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) p[33 * r] = x[r];
+  }
+};
+
 // ---------------------------------------------------------------- plan
 template <int NC>
 struct FftPlan {

@@ -837,75 +837,23 @@ pv_synth_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTab
 #ifndef MLX_KS32
 #define MLX_KS32 1
 #endif
-constexpr double kTwoPi = 6.283185307179586476925286766559;
-MLX_HDC double ks32_cos(double x) {
-  double term = 1.0, sum = 1.0;
-  for (int i = 1; i < 24; ++i) {
-    term *= -x * x / ((2 * i - 1) * (2 * i));
-    sum += term;
-  }
-  return sum;
-}
-MLX_HDC double ks32_sin(double x) {
-  double term = x, sum = x;
-  for (int i = 1; i < 24; ++i) {
-    term *= -x * x / ((2 * i) * (2 * i + 1));
-    sum += term;
-  }
-  return sum;
-}
 struct Rot64 {  // exp(-2 pi i m / 64), m < 16  (c = cos, s = -sin)
   float c[16], s[16];
 };
 MLX_HDC Rot64 make_rot64() {
   Rot64 r{};
   for (int m = 0; m < 16; ++m) {
-    r.c[m] = (float)ks32_cos(kTwoPi * m / 64.0);
-    r.s[m] = (float)-ks32_sin(kTwoPi * m / 64.0);
+    r.c[m] = (float)fft_ccos(6.283185307179586476925286766559 * m / 64.0);
+    r.s[m] = (float)-fft_csin(6.283185307179586476925286766559 * m / 64.0);
   }
   return r;
 }
-struct W32Tab {  // exp(+2 pi i k / 32), k < 16
-  float c[16], s[16];
-};
-MLX_HDC W32Tab make_w32() {
-  W32Tab r{};
-  for (int k = 0; k < 16; ++k) {
-    r.c[k] = (float)ks32_cos(kTwoPi * k / 32.0);
-    r.s[k] = (float)ks32_sin(kTwoPi * k / 32.0);
-  }
-  return r;
-}
-// 32-point DFT with e^{+i...} (inverse direction), natural order in and out: two interleaved 16-point
-// transforms and one radix-2 level
-__device__ __forceinline__ void idft32(cplx<float> (&v)[32]) {
-  using C = cplx<float>;
-  C e[16], o[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    e[i] = v[2 * i];
-    o[i] = v[2 * i + 1];
-  }
-  dft16<+1>(e);
-  dft16<+1>(o);
-  constexpr W32Tab w = make_w32();
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    C tw;
-    if (k == 0) tw = o[k];
-    else if (k == 8) tw = C{-o[k].y, o[k].x};  // * (+i)
-    else tw = C{o[k].x * w.c[k] - o[k].y * w.s[k], o[k].x * w.s[k] + o[k].y * w.c[k]};
-    v[k] = cadd(e[k], tw);
-    v[k + 16] = csub(e[k], tw);
-  }
-}
-MLX_HDC int pad32(int i) { return i + (i >> 5); }
 
 template <int N, bool O16>
 __global__ void __launch_bounds__(128, 3)
 pv_synth32_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvTables tb, const PvScratch sc) {
   constexpr int NC = N / 2, TPF = 32, G = 4, THREADS = 128, H = N / 4, H2 = H / 2, NBP = NC + 32;
-  constexpr int BUF = NC + NC / 32;
+  constexpr int BUF = Fft32x32::BUF;
   constexpr int COLS = H2 / THREADS;
   static_assert(NC == 1024, "two radix-32 stages");
   using C = cplx<float>;
@@ -1039,26 +987,10 @@ pv_synth32_kernel(const PvTrack* __restrict__ tracks, const PvWave wv, const PvT
 #pragma unroll
       for (int m = 16; m < 32; ++m) x[m] = zb[(m - 16) * TPF + t];
       __syncwarp();  // the staging area is overwritten by the first stage's stores
-      idft32(x);     // stage 0: butterfly t on slots x[r] = Z[t + 32 r]; output r goes to position 32 t + r
-      {
-        C* p = zb + 33 * t;  // pad32(32 t + r) = 33 t + r
-#pragma unroll
-        for (int r = 0; r < 32; ++r) p[r] = x[r];
-      }
+      Fft32x32::stage0<+1>(x, zb, t);
       __syncwarp();
-      {
-        const C* p = zb + t;  // pad32(t + 32 r) = t + 33 r
-#pragma unroll
-        for (int r = 0; r < 32; ++r) x[r] = p[33 * r];
-      }
-#pragma unroll
-      for (int r = 1; r < 32; ++r) x[r] = cmul(x[r], p1[r - 1]);
-      idft32(x);  // stage 1: output r is element t + 32 r (natural order, the slots this thread has just read)
-      {
-        C* p = zb + t;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) p[33 * r] = x[r];
-      }
+      Fft32x32::stage1<+1>(x, zb, t, p1);
+      Fft32x32::store(x, zb, t);  // natural order: the slots this thread has just read
     }
     __syncthreads();
 

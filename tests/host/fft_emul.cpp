@@ -81,8 +81,51 @@ int check_all() {
   return bad;
 }
 
+// The 32-points-per-thread plan of the synthesis kernel at fftN = 2048 (Fft32x32: two radix-32 stages, one exchange):
+// 32 emulated threads, the buffer poisoned between the stages.
+template <int DIR>
+int check_32x32() {
+  constexpr int NC = Fft32x32::NC;
+  using C = cplx<float>;
+  std::vector<double> in(2 * NC), ref(2 * NC), scratch(4 * NC);
+  srand(77 + DIR);
+  for (auto& v : in) v = (rand() / (double)RAND_MAX) * 2.0 - 1.0;
+  mlxo_fft_plan* plan = mlxo_fft_plan_create(NC);
+  mlxo_fft_c2c(plan, in.data(), ref.data(), scratch.data(), DIR);
+  mlxo_fft_plan_destroy(plan);
+  std::vector<C> regs(32 * 32), buf(Fft32x32::BUF, C{NAN, NAN});
+  for (int t = 0; t < 32; ++t)
+    for (int r = 0; r < 32; ++r) regs[t * 32 + r] = C{(float)in[2 * (t + 32 * r)], (float)in[2 * (t + 32 * r) + 1]};
+  for (int t = 0; t < 32; ++t) Fft32x32::stage0<DIR>(*reinterpret_cast<C(*)[32]>(&regs[t * 32]), buf.data(), t);
+  int bad = 0;
+  for (int t = 0; t < 32; ++t) {
+    C p1[31];
+    for (int r = 1; r < 32; ++r) {
+      const double a = DIR * 2.0 * M_PI * (double)((t * r) % NC) / NC;
+      p1[r - 1] = C{(float)std::cos(a), (float)std::sin(a)};
+    }
+    Fft32x32::stage1<DIR>(*reinterpret_cast<C(*)[32]>(&regs[t * 32]), buf.data(), t, p1);
+  }
+  for (auto& v : buf) v = C{NAN, NAN};
+  for (int t = 0; t < 32; ++t) Fft32x32::store(*reinterpret_cast<C(*)[32]>(&regs[t * 32]), buf.data(), t);
+  double err = 0, nrm = 0;
+  for (int i = 0; i < NC; ++i) {
+    const C v = buf[pad32(i)];  // natural order, padded: what the overlap-add reads
+    const C w = regs[(i % 32) * 32 + i / 32];
+    if (!(v.x == w.x && v.y == w.y)) ++bad;
+    const double dx = v.x - ref[2 * i], dy = v.y - ref[2 * i + 1];
+    err += dx * dx + dy * dy;
+    nrm += ref[2 * i] * ref[2 * i] + ref[2 * i + 1] * ref[2 * i + 1];
+  }
+  const double rel = std::sqrt(err / nrm);
+  std::printf("32 x 32 plan, DIR %+d: rel rms %.2e  bad %d\n", DIR, rel, bad);
+  return (bad != 0) || !(rel < 2e-6);
+}
+
 int main() {
   int bad = 0;
+  bad |= check_32x32<+1>();
+  bad |= check_32x32<-1>();
   bad |= check_all<256>();
   bad |= check_all<512>();
   bad |= check_all<1024>();
